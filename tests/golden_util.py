@@ -1,0 +1,29 @@
+"""Helpers shared by the CPU (oracle) and GPU (CUDA path) golden-rollout tests."""
+import glob
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+HCOLS = ("px", "py", "vx", "vy", "theta", "gx", "gy", "fgx", "fgy", "vpref", "radius")
+RCOLS = ("rpx", "rpy", "rvx", "rvy", "rtheta", "rgx", "rgy")
+DOOR_SIMS = ("hallway_static", "hallway_static_with_back", "hallway_bottleneck")
+
+
+def rollout_files():
+    return sorted(glob.glob(os.path.join(GOLDEN, "rollout_*.npz")))
+
+
+def load_rollout(path):
+    g = dict(np.load(path, allow_pickle=False))
+    g["name"] = os.path.basename(path)[len("rollout_"):-4]
+    for k in ("human_policy", "sim"):
+        g[k] = str(g[k])
+    return g
+
+
+def door_params(g):
+    """(enabled, door_y_mid_min, door_y_mid_max, door_x_mid, door_y_min, door_y_max, door_width)"""
+    enabled = g["sim"] in DOOR_SIMS and len(g["segs"]) > 0
+    d = np.nan_to_num(g["door"], nan=0.0)
+    return (int(enabled),) + tuple(float(x) for x in d)
