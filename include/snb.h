@@ -1,0 +1,205 @@
+/*
+ * include/snb.h -- C ABI of libsnb.so, the B200-native replacement for the data-parallel hot path of
+ * sepsamavi/safe-interactive-crowdnav (CrowdSimPlus per-agent ORCA/SFM step + JMID denoising loop).
+ *
+ * Boundary rules
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - pointers named *_dev are CUDA device pointers owned by the caller (e.g. torch.Tensor.data_ptr());
+ *     pointers named *_host are ordinary host memory.  `stream` is a cudaStream_t passed as void* (NULL =
+ *     the legacy default stream).  Device entry points are asynchronous with respect to `stream`.
+ *   - every function returns 0 (SNB_OK) or a negative SNB_E* code and never throws; the message of the
+ *     last failure on the calling thread is available from snb_last_error().
+ *   - there is NO CPU fallback: if no CUDA device / kernel image is usable the call fails with SNB_ECUDA.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference root).
+ */
+#ifndef SNB_H
+#define SNB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNB_VERSION 100 /* 0.1.0 */
+
+enum {
+    SNB_OK = 0,
+    SNB_EINVAL = -1,       /* bad argument (NULL, size, alignment) */
+    SNB_ECUDA = -2,        /* CUDA runtime / driver error, no device, launch failure */
+    SNB_EUNSUPPORTED = -3, /* size beyond a compiled limit (see SNB_MAX_*) */
+    SNB_ENOMEM = -4,
+    SNB_EOVERFLOW = -5     /* a device-side capacity (ORCA lines, obstacle neighbours) was exceeded */
+};
+
+int snb_version(void);
+const char *snb_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches counter) */
+uint64_t snb_launch_count(void);
+
+/* ======================================================================================================
+ * Crowd step  (crowd_sim_plus/envs/crowd_sim_plus.py:1025-1257, envs/policy/{orca,orca_plus,social_force}.py)
+ * ====================================================================================================== */
+
+enum { SNB_POLICY_ORCA = 0, SNB_POLICY_ORCA_PLUS = 1, SNB_POLICY_SFM = 2 };
+enum { SNB_KIN_HOLONOMIC = 0, SNB_KIN_UNICYCLE = 1 };
+
+#define SNB_MAX_AGENTS_PER_ENV 32 /* humans + observed extras handled by one warp */
+#define SNB_MAX_ORCA_LINES 32
+#define SNB_MAX_SEGMENTS 64
+
+/* Attributes of the reference policy objects: ORCA.__init__ (orca.py:55-67), ORCAPlus.configure
+ * (orca_plus.py:15-27), SFM.configure (social_force.py:21-36), plus [env] time_step. */
+typedef struct SnbPolicyCfg {
+    int32_t policy;      /* SNB_POLICY_* */
+    int32_t max_neighbors;
+    double time_step;
+    double neighbor_dist, time_horizon, time_horizon_obst;
+    double policy_radius; /* PyRVOSimulator default radius (never used by an agent) */
+    double max_speed;     /* max speed given to every OTHER agent of the throw-away simulator */
+    double safety_space;
+    double sfm_radius, A, B, KI, A_static, B_static, A_bottleneck, B_bottleneck;
+    int32_t is_bottleneck;
+    int32_t _pad;
+} SnbPolicyCfg;
+
+/* Human.get_g_xy door logic (envs/utils/human_plus.py:19-52) */
+typedef struct SnbDoorCfg {
+    int32_t enabled, _pad;
+    double door_y_mid_min, door_y_mid_max, door_x_mid, door_y_min, door_y_max, door_width;
+} SnbDoorCfg;
+
+/* reward table of CrowdSimPlus.configure (crowd_sim_plus.py:87-128) */
+typedef struct SnbRewardCfg {
+    double success_reward, timeout, collision_penalty, wall_collision_penalty, freezing_penalty;
+    int32_t discomfort, has_progress;
+    double discomfort_dist, discomfort_penalty_factor, progress_factor, time_limit;
+} SnbRewardCfg;
+
+/* flag bits written per environment by snb_env_step (the non-zero info[...] entries of step()) */
+enum {
+    SNB_F_REACHED = 1, SNB_F_TIMEOUT = 2, SNB_F_COLLISION = 4, SNB_F_WALL = 8,
+    SNB_F_FROZEN = 16, SNB_F_DANGER = 32, SNB_F_DONE = 64
+};
+
+/*
+ * SoA state of B environments in HBM, all fp64 (the reference's Python floats; ORCA narrows to fp32 exactly
+ * where Python-RVO2 does).  Humans: [B*H] arrays, element b*H+i.  "Extras" are the agents a human observes
+ * after the other humans, in `ob` order (crowd_sim_plus.py:1047-1049): [B*E] arrays.  In the simulator E=1
+ * and extra 0 IS the robot (its px/py/vx/vy are updated by snb_env_step); in the B=1 plugin call E = number
+ * of observed agents.  Replaces the FullState / ObservableState / JointState objects
+ * (envs/utils/state_plus.py:1-66).
+ */
+typedef struct SnbCrowdState {
+    int32_t B, H, E;
+    int32_t n_obs_extras;          /* how many extras the humans see (0 = robot invisible) */
+    double *px, *py, *vx, *vy, *theta, *gx, *gy, *fgx, *fgy, *vpref, *radius, *human_time; /* [B*H] */
+    double *ex_px, *ex_py, *ex_vx, *ex_vy, *ex_radius;                                     /* [B*E] */
+    double *rtheta, *rgx, *rgy, *global_time, *prev_dist;                                  /* [B] (env step only) */
+    int32_t robot_kinematics, _pad;
+} SnbCrowdState;
+
+/* Static line-segment obstacles shared by all environments (crowd_sim_plus.py:322-422).  Creation runs the
+ * RVO2 obstacle pre-processing (addObstacle + processObstacles, orca_plus.py:50-53) ONCE on the host and
+ * uploads the vertex list + BSP tree; the reference redoes it per human per step. */
+typedef struct SnbObstacles SnbObstacles;
+int snb_obstacles_create(SnbObstacles **out, const double *segs_host /* [n_seg*4] x1,y1,x2,y2 */, int32_t n_seg);
+int snb_obstacles_destroy(SnbObstacles *obs);
+int32_t snb_obstacles_num_vertices(const SnbObstacles *obs);
+/* out7 = point.x point.y unitDir.x unitDir.y next prev isConvex (float), for parity tests of the BSP split */
+int snb_obstacles_get_vertex(const SnbObstacles *obs, int32_t i, float *out7_host);
+
+/*
+ * Human policy for every human of every environment, no clamp / integration:
+ *   ORCA.predict (orca.py:82-133), ORCAPlus.predict (orca_plus.py:29-90), SFM.predict (social_force.py:38-94)
+ * batched over B*H agents.  out_v_dev [B*H*2] (vx,vy).  Optional (ORCA only): nbr_dev [B*H*max_neighbors]
+ * agent ids in RVO2 neighbour order (human j -> j, extra e -> H+e; -1 padded) and nbr_cnt_dev [B*H].
+ * status_dev (optional, int32[1]) receives a non-zero SNB_EOVERFLOW marker if a device capacity was exceeded.
+ */
+int snb_policy_step(const SnbPolicyCfg *cfg, const SnbCrowdState *state, const SnbObstacles *obs /* may be NULL */,
+                    double *out_v_dev, int32_t *nbr_dev, int32_t *nbr_cnt_dev, int32_t *status_dev, void *stream);
+
+/*
+ * One CrowdSimPlus.step(action, update=True) for B environments in ONE launch: human policies, static-obstacle
+ * clamp (constrain_agent_action_exact, crowd_sim_plus.py:869-989), robot clamp + wall flag, robot-human
+ * collision scan, frozen / goal / time-out, reward, state integration (Agent.step agent_plus.py:199-214,
+ * Human.step human_plus.py:118-120), clocks and human arrival times.  State is updated in place.
+ * robot_action_dev [B*2] = (vx,vy) or (v,r).  active_dev (optional uint8[B]): environments with 0 are skipped.
+ * Outputs (each optional): reward_dev[B], dmin_dev[B], flags_dev[B] (SNB_F_*), nbr_dev / nbr_cnt_dev as above.
+ */
+int snb_env_step(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const SnbRewardCfg *reward_cfg,
+                 const SnbCrowdState *state, const SnbObstacles *obs, const double *robot_action_dev,
+                 const uint8_t *active_dev, double *reward_dev, double *dmin_dev, int32_t *flags_dev,
+                 int32_t *nbr_dev, int32_t *nbr_cnt_dev, int32_t *status_dev, void *stream);
+
+/*
+ * Host-buffer form of one policy call -- the literal replacement of what `policy.predict(state)` does behind
+ * the rvo2 FFI (PyRVOSimulator(...) / addAgent / setAgentPrefVelocity / doStep / getAgentVelocity,
+ * orca.py:95-129) or inside SFM.predict: copies the JointState to the device, runs the same kernel with
+ * B=1,H=1,E=n_others, copies the action back, synchronises.
+ *   self8 = px,py,vx,vy,radius,gx,gy,v_pref ; others5 = n x (px,py,vx,vy,radius) ; segs = m x (x1,y1,x2,y2)
+ */
+int snb_policy_predict_host(const SnbPolicyCfg *cfg, const double *self8_host, int32_t n_others,
+                            const double *others5_host, int32_t n_seg, const double *segs_host,
+                            double *out_v2_host, int32_t *nbr_ids_host /* [max_neighbors] ob indices, may be NULL */,
+                            int32_t *n_nbr_host);
+
+/* ======================================================================================================
+ * JMID / iMID denoiser  (sicnav_diffusion/JMID/MID/models/diffusion.py:153-209, 478-541)
+ * ====================================================================================================== */
+
+/* fp32 device pointers into the reference state_dict; layouts as stored by torch
+ * (nn.Linear weight = [out,in] row-major). */
+typedef struct SnbCslWeights { /* ConcatSquashLinear, models/common.py:58-72 */
+    const float *layer_w, *layer_b, *hyper_bias_w, *hyper_gate_w, *hyper_gate_b;
+} SnbCslWeights;
+
+typedef struct SnbEncLayerWeights { /* nn.TransformerEncoderLayer(512, 4, 1024), post-norm */
+    const float *in_proj_w, *in_proj_b, *out_proj_w, *out_proj_b, *lin1_w, *lin1_b, *lin2_w, *lin2_b,
+        *norm1_w, *norm1_b, *norm2_w, *norm2_b;
+} SnbEncLayerWeights;
+
+typedef struct SnbJmidWeights {
+    SnbCslWeights concat1, concat3, concat4, linear;
+    SnbEncLayerWeights layers[3];
+    const float *pos_emb; /* [>=T,512] rows of net.pos_emb.pe */
+    const float *betas, *alpha_bars; /* [101] var_sched buffers */
+} SnbJmidWeights;
+
+typedef struct SnbJmid SnbJmid;
+
+/* Builds the device-resident model: converts the GEMM weights to bf16, allocates every activation buffer for
+ * up to `max_envs` environments of A agents x S samples x T steps (no allocation happens afterwards).
+ * joint=1: JointPredictionTransformerConcatLinear (one sequence of T*A*S tokens per env, quirk q1);
+ * joint=0: TransformerConcatLinear (A*S sequences of T tokens).   Replaces MID._build_model (mid.py:1270-1297). */
+int snb_jmid_create(SnbJmid **out, const SnbJmidWeights *w_dev, int32_t max_envs, int32_t A, int32_t S, int32_t T,
+                    int32_t joint, void *stream);
+int snb_jmid_destroy(SnbJmid *h);
+
+/*
+ * DiffusionTraj.sample_sicnav_inference (diffusion.py:478-541), DDIM, batched over B environments:
+ *   ctx_dev  [B,A,256] fp32   context of each agent (Trajectron encoder output)
+ *   x_T_dev  [B,S*A,T,2] fp32 initial noise, row r = s*A + a (injected; the reference draws torch.randn, quirk q2)
+ *   out_vel_dev [B,S,A,T,2] fp32 velocities x_0
+ * n_steps = the yaml `step_size` (stride = int(100/n_steps), t = 100, 100-stride, ..., stride).
+ */
+int snb_jmid_denoise(SnbJmid *h, const float *ctx_dev, const float *x_T_dev, float *out_vel_dev, int32_t B,
+                     int32_t n_steps, void *stream);
+/* one noise-network forward at diffusion step t (parity of JointPredictionTransformerConcatLinear.forward) */
+int snb_jmid_eps(SnbJmid *h, const float *ctx_dev, const float *x_t_dev, float *eps_dev, int32_t B, int32_t t,
+                 void *stream);
+/* SingleIntegrator.integrate_samples (single_integrator.py:290-321): pos = cumsum_t(v)*dt + p0[a].
+ * vel_dev [B,S,A,T,2], p0_dev [B,A,2] -> pos_dev [B,S,A,T,2] */
+int snb_jmid_integrate(const float *vel_dev, const float *p0_dev, float *pos_dev, int32_t B, int32_t S, int32_t A,
+                       int32_t T, float dt, void *stream);
+/* host-buffer form: H2D(ctx, x_T) -> denoise -> integrate -> D2H(pos), synchronous (the predictor plugin path) */
+int snb_jmid_predict_host(SnbJmid *h, const float *ctx_host, const float *x_T_host, const float *p0_host,
+                          float *pos_host, int32_t B, int32_t n_steps, float dt);
+/* algorithmic FLOPs of one denoise iteration for one environment */
+double snb_jmid_flops_per_iter(int32_t A, int32_t S, int32_t T, int32_t joint);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNB_H */

@@ -1,0 +1,1361 @@
+// csrc/crowd_kernels.cu -- the CrowdSimPlus per-agent step on sm_100a.
+//
+// One launch = one CrowdSimPlus.step for B independent environments (reference:
+// crowd_sim_plus/envs/crowd_sim_plus.py:1025-1257).  Design:
+//   * a CTA owns a tile of EPC consecutive environments; their fp64 SoA state is staged into shared memory
+//     by 1-D TMA bulk copies (cp.async.bulk + mbarrier), one per state array;
+//   * one WARP per human evaluates the policy: lanes = the other agents.  ORCA: each lane builds one
+//     neighbour's half-plane, the incremental 2-D LP runs warp-cooperatively (the scan over previous lines in
+//     linearProgram1 is a shuffle min/max reduction).  SFM: each lane adds one pairwise / wall force and the
+//     sum is a shuffle reduction;
+//   * phase 2 (one thread per agent / per environment): static-obstacle clamp, robot collision scan, reward,
+//     flags, integration, written back coalesced.
+// Numerics: this file is compiled with -fmad=false.  ORCA runs in fp32 exactly where Python-RVO2 does (every
+// float op is a single IEEE op in the order of RVO2's Agent.cpp) so it is bit-identical to oracle/rvo2_oracle.c;
+// everything else is fp64 like the reference's Python, with explicit fma() only where numpy's BLAS dot fuses.
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "snb_common.h"
+
+#define RVO_EPSILON 0.00001f
+#define FULL 0xffffffffu
+
+// ---------------------------------------------------------------------------------------------------------
+// obstacle data (host-built, device-resident)
+// ---------------------------------------------------------------------------------------------------------
+struct ObstVert { float px, py, ux, uy; int next, prev, convex, pad; };
+struct BspNode { int obstacle, left, right, pad; };
+
+struct SnbObstacles {
+    int n_seg = 0;
+    std::vector<double> segs;      // host copy [n_seg*4]
+    std::vector<ObstVert> verts;   // after BSP splitting
+    std::vector<BspNode> nodes;
+    int root = -1;
+    double *d_segs = nullptr;
+    ObstVert *d_verts = nullptr;
+    BspNode *d_nodes = nullptr;
+};
+
+// ---- host float helpers, same op order as RVO2's Vector2.h (this TU is built with -fmad=false; the host
+// compiler gets -ffp-contract=off through -Xcompiler) ----
+namespace hostrvo {
+struct V2 { float x, y; };
+static inline V2 sub(V2 a, V2 b) { return {a.x - b.x, a.y - b.y}; }
+static inline float det(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }
+static inline float leftOf(V2 a, V2 b, V2 c) { return det(sub(a, c), sub(b, a)); }
+static inline V2 normalize(V2 a) { const float inv = 1.0f / sqrtf(a.x * a.x + a.y * a.y); return {a.x * inv, a.y * inv}; }
+
+// KdTree::buildObstacleTreeRecursive (RVO2 KdTree.cpp).  Returns node index or -1.
+static int buildObstacleTree(SnbObstacles &o, const std::vector<int> &obstacles)
+{
+    if (obstacles.empty()) return -1;
+    const size_t n = obstacles.size();
+    size_t optimalSplit = 0, minLeft = n, minRight = n;
+    auto worse_or_equal = [](size_t l, size_t r, size_t ml, size_t mr) {
+        const size_t a1 = std::max(l, r), a2 = std::min(l, r), b1 = std::max(ml, mr), b2 = std::min(ml, mr);
+        return !(a1 < b1 || (a1 == b1 && a2 < b2));
+    };
+    for (size_t i = 0; i < n; ++i) {
+        size_t leftSize = 0, rightSize = 0;
+        const V2 i1{o.verts[obstacles[i]].px, o.verts[obstacles[i]].py};
+        const ObstVert &vi2 = o.verts[o.verts[obstacles[i]].next];
+        const V2 i2{vi2.px, vi2.py};
+        for (size_t j = 0; j < n; ++j) {
+            if (i == j) continue;
+            const V2 j1{o.verts[obstacles[j]].px, o.verts[obstacles[j]].py};
+            const ObstVert &vj2 = o.verts[o.verts[obstacles[j]].next];
+            const V2 j2{vj2.px, vj2.py};
+            const float j1LeftOfI = leftOf(i1, i2, j1), j2LeftOfI = leftOf(i1, i2, j2);
+            if (j1LeftOfI >= -RVO_EPSILON && j2LeftOfI >= -RVO_EPSILON) ++leftSize;
+            else if (j1LeftOfI <= RVO_EPSILON && j2LeftOfI <= RVO_EPSILON) ++rightSize;
+            else { ++leftSize; ++rightSize; }
+            if (worse_or_equal(leftSize, rightSize, minLeft, minRight)) break;
+        }
+        if (!worse_or_equal(leftSize, rightSize, minLeft, minRight)) { minLeft = leftSize; minRight = rightSize; optimalSplit = i; }
+    }
+    std::vector<int> leftObst, rightObst;
+    const size_t i = optimalSplit;
+    const int I1 = obstacles[i];
+    for (size_t j = 0; j < n; ++j) {
+        if (i == j) continue;
+        const int J1 = obstacles[j];
+        const int J2 = o.verts[J1].next;
+        const int I2 = o.verts[I1].next;
+        const V2 i1{o.verts[I1].px, o.verts[I1].py}, i2{o.verts[I2].px, o.verts[I2].py};
+        const V2 j1{o.verts[J1].px, o.verts[J1].py}, j2{o.verts[J2].px, o.verts[J2].py};
+        const float j1LeftOfI = leftOf(i1, i2, j1), j2LeftOfI = leftOf(i1, i2, j2);
+        if (j1LeftOfI >= -RVO_EPSILON && j2LeftOfI >= -RVO_EPSILON) leftObst.push_back(J1);
+        else if (j1LeftOfI <= RVO_EPSILON && j2LeftOfI <= RVO_EPSILON) rightObst.push_back(J1);
+        else {
+            const float t = det(sub(i2, i1), sub(j1, i1)) / det(sub(i2, i1), sub(j1, j2));
+            const V2 d = sub(j2, j1);
+            ObstVert nv{};
+            nv.px = j1.x + t * d.x; nv.py = j1.y + t * d.y;
+            nv.prev = J1; nv.next = J2; nv.convex = 1;
+            nv.ux = o.verts[J1].ux; nv.uy = o.verts[J1].uy;
+            const int nid = (int)o.verts.size();
+            o.verts.push_back(nv);
+            o.verts[J1].next = nid; o.verts[J2].prev = nid;
+            if (j1LeftOfI > 0.0f) { leftObst.push_back(J1); rightObst.push_back(nid); }
+            else { rightObst.push_back(J1); leftObst.push_back(nid); }
+        }
+    }
+    const int me = (int)o.nodes.size();
+    o.nodes.push_back(BspNode{I1, -1, -1, 0});
+    const int l = buildObstacleTree(o, leftObst);
+    const int r = buildObstacleTree(o, rightObst);
+    o.nodes[me].left = l; o.nodes[me].right = r;
+    return me;
+}
+} // namespace hostrvo
+
+extern "C" int snb_obstacles_create(SnbObstacles **out, const double *segs, int32_t n_seg)
+{
+    SNB_REQUIRE(out != nullptr, SNB_EINVAL, "snb_obstacles_create: out is NULL");
+    SNB_REQUIRE(n_seg >= 0 && n_seg <= SNB_MAX_SEGMENTS, SNB_EUNSUPPORTED, "snb_obstacles_create: n_seg=%d beyond SNB_MAX_SEGMENTS", n_seg);
+    SNB_REQUIRE(n_seg == 0 || segs != nullptr, SNB_EINVAL, "snb_obstacles_create: segs is NULL");
+    SnbObstacles *o = new SnbObstacles();
+    o->n_seg = n_seg;
+    o->segs.assign(segs, segs + 4 * (size_t)n_seg);
+    // RVOSimulator::addObstacle for every 2-vertex wall, in segment order (orca_plus.py:50-51)
+    for (int k = 0; k < n_seg; ++k) {
+        const hostrvo::V2 p0{(float)segs[4 * k], (float)segs[4 * k + 1]}, p1{(float)segs[4 * k + 2], (float)segs[4 * k + 3]};
+        const int id0 = (int)o->verts.size(), id1 = id0 + 1;
+        const hostrvo::V2 u0 = hostrvo::normalize(hostrvo::sub(p1, p0)), u1 = hostrvo::normalize(hostrvo::sub(p0, p1));
+        o->verts.push_back(ObstVert{p0.x, p0.y, u0.x, u0.y, id1, id1, 1, 0});
+        o->verts.push_back(ObstVert{p1.x, p1.y, u1.x, u1.y, id0, id0, 1, 0});
+    }
+    if (n_seg > 0) { // processObstacles (orca_plus.py:52-53)
+        std::vector<int> all(o->verts.size());
+        for (size_t i = 0; i < all.size(); ++i) all[i] = (int)i;
+        o->root = hostrvo::buildObstacleTree(*o, all);
+        cudaError_t e = cudaMalloc(&o->d_segs, sizeof(double) * 4 * (size_t)n_seg);
+        if (e == cudaSuccess) e = cudaMalloc(&o->d_verts, sizeof(ObstVert) * o->verts.size());
+        if (e == cudaSuccess) e = cudaMalloc(&o->d_nodes, sizeof(BspNode) * o->nodes.size());
+        if (e == cudaSuccess) e = cudaMemcpy(o->d_segs, o->segs.data(), sizeof(double) * 4 * (size_t)n_seg, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(o->d_verts, o->verts.data(), sizeof(ObstVert) * o->verts.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(o->d_nodes, o->nodes.data(), sizeof(BspNode) * o->nodes.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            snb_set_error("snb_obstacles_create: %s", cudaGetErrorString(e));
+            snb_obstacles_destroy(o);
+            return SNB_ECUDA;
+        }
+    }
+    *out = o;
+    return SNB_OK;
+}
+
+extern "C" int snb_obstacles_destroy(SnbObstacles *o)
+{
+    if (!o) return SNB_OK;
+    cudaFree(o->d_segs); cudaFree(o->d_verts); cudaFree(o->d_nodes);
+    delete o;
+    return SNB_OK;
+}
+
+extern "C" int32_t snb_obstacles_num_vertices(const SnbObstacles *o) { return o ? (int32_t)o->verts.size() : 0; }
+
+extern "C" int snb_obstacles_get_vertex(const SnbObstacles *o, int32_t i, float *out7)
+{
+    SNB_REQUIRE(o && out7 && i >= 0 && i < (int)o->verts.size(), SNB_EINVAL, "snb_obstacles_get_vertex: bad index");
+    const ObstVert &v = o->verts[i];
+    out7[0] = v.px; out7[1] = v.py; out7[2] = v.ux; out7[3] = v.uy; out7[4] = (float)v.next; out7[5] = (float)v.prev; out7[6] = (float)v.convex;
+    return SNB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device code
+// ---------------------------------------------------------------------------------------------------------
+struct CrowdParams {
+    SnbPolicyCfg cfg;
+    SnbDoorCfg door;
+    SnbRewardCfg rcfg;
+    SnbCrowdState st;
+    const double *robot_action;
+    const uint8_t *active;
+    double *reward, *dmin, *out_v;
+    int *flags, *nbr, *nbr_cnt, *status;
+    int n_seg;
+    const double *segs;
+    int n_vert;
+    const ObstVert *verts;
+    const BspNode *nodes;
+    int bsp_root;
+    int epc;       // environments per CTA
+    int full_step; // 0 = policy only, 1 = CrowdSimPlus.step
+};
+
+struct Line { float px, py, dx, dy; };
+
+__device__ __forceinline__ float det2(float ax, float ay, float bx, float by) { return ax * by - ay * bx; }
+__device__ __forceinline__ float dot2(float ax, float ay, float bx, float by) { return ax * bx + ay * by; }
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ Line shfl_line(const Line &l, int src) {
+    Line r;
+    r.px = __shfl_sync(FULL, l.px, src); r.py = __shfl_sync(FULL, l.py, src);
+    r.dx = __shfl_sync(FULL, l.dx, src); r.dy = __shfl_sync(FULL, l.dy, src);
+    return r;
+}
+
+// RVO2 linearProgram2 with linearProgram1 inlined, executed by a whole warp (Agent.cpp).
+// Lane k holds line k (k < n <= 32).  `rx, ry` are warp-uniform.  The scan over the previous lines of
+// linearProgram1 becomes a min/max shuffle reduction: tLeft only grows and tRight only shrinks along the scan,
+// so "some prefix has tLeft > tRight" == "the final pair has", and min/max are exact, hence the result is
+// bit-identical to the sequential program.
+__device__ int lp2_warp(const Line &my, int n, float radius, float optx, float opty, bool dirOpt, float &rx, float &ry, int lane)
+{
+    if (dirOpt) { rx = optx * radius; ry = opty * radius; }
+    else if (dot2(optx, opty, optx, opty) > radius * radius) {
+        const float inv = 1.0f / sqrtf(dot2(optx, opty, optx, opty));
+        const float nx = optx * inv, ny = opty * inv;
+        rx = nx * radius; ry = ny * radius;
+    } else { rx = optx; ry = opty; }
+
+    for (int i = 0; i < n; ++i) {
+        const Line li = shfl_line(my, i);
+        if (det2(li.dx, li.dy, li.px - rx, li.py - ry) > 0.0f) {
+            const float tx = rx, ty = ry;
+            const float dotProduct = dot2(li.px, li.py, li.dx, li.dy);
+            const float discriminant = dotProduct * dotProduct + radius * radius - dot2(li.px, li.py, li.px, li.py);
+            bool fail = discriminant < 0.0f;
+            float tLeft = 0.f, tRight = 0.f;
+            if (!fail) {
+                const float sq = sqrtf(discriminant);
+                tLeft = -dotProduct - sq;
+                tRight = -dotProduct + sq;
+                float myL = -INFINITY, myR = INFINITY;
+                bool pfail = false;
+                if (lane < i) {
+                    const float denominator = det2(li.dx, li.dy, my.dx, my.dy);
+                    const float numerator = det2(my.dx, my.dy, li.px - my.px, li.py - my.py);
+                    if (fabsf(denominator) <= RVO_EPSILON) { if (numerator < 0.0f) pfail = true; }
+                    else {
+                        const float t = numerator / denominator;
+                        if (denominator >= 0.0f) myR = t; else myL = t;
+                    }
+                }
+                tRight = fminf(tRight, warp_min(myR));
+                tLeft = fmaxf(tLeft, warp_max(myL));
+                fail = (__any_sync(FULL, pfail) != 0) || (tLeft > tRight);
+            }
+            if (fail) { rx = tx; ry = ty; return i; }
+            if (dirOpt) {
+                if (dot2(optx, opty, li.dx, li.dy) > 0.0f) { rx = li.px + tRight * li.dx; ry = li.py + tRight * li.dy; }
+                else { rx = li.px + tLeft * li.dx; ry = li.py + tLeft * li.dy; }
+            } else {
+                const float t = dot2(li.dx, li.dy, optx - li.px, opty - li.py);
+                if (t < tLeft) { rx = li.px + tLeft * li.dx; ry = li.py + tLeft * li.dy; }
+                else if (t > tRight) { rx = li.px + tRight * li.dx; ry = li.py + tRight * li.dy; }
+                else { rx = li.px + t * li.dx; ry = li.py + t * li.dy; }
+            }
+        }
+    }
+    return n;
+}
+
+// RVO2 linearProgram3, warp-cooperative.  `scratch` = 32 Lines of per-warp shared memory.
+__device__ void lp3_warp(const Line &my, int n, int numObstLines, int beginLine, float radius, float &rx, float &ry,
+                         int lane, Line *scratch)
+{
+    float distance = 0.0f;
+    for (int i = beginLine; i < n; ++i) {
+        const Line li = shfl_line(my, i);
+        if (det2(li.dx, li.dy, li.px - rx, li.py - ry) > distance) {
+            bool have = false;
+            Line pl = my;
+            if (lane < numObstLines) have = true;
+            else if (lane < i) {
+                const float determinant = det2(li.dx, li.dy, my.dx, my.dy);
+                have = true;
+                if (fabsf(determinant) <= RVO_EPSILON) {
+                    if (dot2(li.dx, li.dy, my.dx, my.dy) > 0.0f) have = false;
+                    else { pl.px = 0.5f * (li.px + my.px); pl.py = 0.5f * (li.py + my.py); }
+                } else {
+                    const float s = det2(my.dx, my.dy, li.px - my.px, li.py - my.py) / determinant;
+                    pl.px = li.px + s * li.dx; pl.py = li.py + s * li.dy;
+                }
+                if (have) {
+                    const float vx = my.dx - li.dx, vy = my.dy - li.dy;
+                    const float inv = 1.0f / sqrtf(dot2(vx, vy, vx, vy));
+                    pl.dx = vx * inv; pl.dy = vy * inv;
+                }
+            }
+            const unsigned mask = __ballot_sync(FULL, have);
+            const int np = __popc(mask);
+            if (have) scratch[__popc(mask & ((1u << lane) - 1u))] = pl;
+            __syncwarp();
+            Line mine = (lane < np) ? scratch[lane] : Line{0.f, 0.f, 1.f, 0.f};
+            __syncwarp();
+            const float tx = rx, ty = ry;
+            if (lp2_warp(mine, np, radius, -li.dy, li.dx, true, rx, ry, lane) < np) { rx = tx; ry = ty; }
+            distance = det2(li.dx, li.dy, li.px - rx, li.py - ry);
+        }
+    }
+}
+
+// Agent ORCA half-plane for one neighbour (Agent::computeNewVelocity agent part).
+__device__ Line agent_orca_line(float px, float py, float vx, float vy, float radius, float opx, float opy, float ovx,
+                                float ovy, float orad, float invTimeHorizon, float timeStep)
+{
+    const float rpx = opx - px, rpy = opy - py;
+    const float rvx = vx - ovx, rvy = vy - ovy;
+    const float distSq = dot2(rpx, rpy, rpx, rpy);
+    const float combinedRadius = radius + orad;
+    const float combinedRadiusSq = combinedRadius * combinedRadius;
+    Line line;
+    float ux, uy;
+    if (distSq > combinedRadiusSq) {
+        const float wx = rvx - invTimeHorizon * rpx, wy = rvy - invTimeHorizon * rpy;
+        const float wLengthSq = dot2(wx, wy, wx, wy);
+        const float dotProduct1 = dot2(wx, wy, rpx, rpy);
+        if (dotProduct1 < 0.0f && dotProduct1 * dotProduct1 > combinedRadiusSq * wLengthSq) {
+            const float wLength = sqrtf(wLengthSq);
+            const float inv = 1.0f / wLength;
+            const float unx = wx * inv, uny = wy * inv;
+            line.dx = uny; line.dy = -unx;
+            const float s = combinedRadius * invTimeHorizon - wLength;
+            ux = s * unx; uy = s * uny;
+        } else {
+            const float leg = sqrtf(distSq - combinedRadiusSq);
+            const float inv = 1.0f / distSq;
+            if (det2(rpx, rpy, wx, wy) > 0.0f) {
+                line.dx = (rpx * leg - rpy * combinedRadius) * inv;
+                line.dy = (rpx * combinedRadius + rpy * leg) * inv;
+            } else {
+                line.dx = -((rpx * leg + rpy * combinedRadius) * inv);
+                line.dy = -((-rpx * combinedRadius + rpy * leg) * inv);
+            }
+            const float dotProduct2 = dot2(rvx, rvy, line.dx, line.dy);
+            ux = dotProduct2 * line.dx - rvx; uy = dotProduct2 * line.dy - rvy;
+        }
+    } else {
+        const float invTimeStep = 1.0f / timeStep;
+        const float wx = rvx - invTimeStep * rpx, wy = rvy - invTimeStep * rpy;
+        const float wLength = sqrtf(dot2(wx, wy, wx, wy));
+        const float inv = 1.0f / wLength;
+        const float unx = wx * inv, uny = wy * inv;
+        line.dx = uny; line.dy = -unx;
+        const float s = combinedRadius * invTimeStep - wLength;
+        ux = s * unx; uy = s * uny;
+    }
+    line.px = vx + 0.5f * ux; line.py = vy + 0.5f * uy;
+    return line;
+}
+
+// Obstacle ORCA half-plane for obstacle neighbour `o1i` (Agent::computeNewVelocity obstacle part).
+// Returns false when RVO2 `continue`s without adding a line.
+__device__ bool obstacle_orca_line(const ObstVert *verts, int o1i, float px, float py, float vx, float vy, float radius,
+                                   float invT, Line &line)
+{
+    int o2i = verts[o1i].next;
+    ObstVert o1 = verts[o1i], o2 = verts[o2i];
+    const float rp1x = o1.px - px, rp1y = o1.py - py, rp2x = o2.px - px, rp2y = o2.py - py;
+    const float distSq1 = dot2(rp1x, rp1y, rp1x, rp1y), distSq2 = dot2(rp2x, rp2y, rp2x, rp2y);
+    const float radiusSq = radius * radius;
+    const float ovx = o2.px - o1.px, ovy = o2.py - o1.py;
+    const float s = dot2(-rp1x, -rp1y, ovx, ovy) / dot2(ovx, ovy, ovx, ovy);
+    const float tx_ = -rp1x - s * ovx, ty_ = -rp1y - s * ovy;
+    const float distSqLine = dot2(tx_, ty_, tx_, ty_);
+
+    if (s < 0.0f && distSq1 <= radiusSq) {
+        if (o1.convex) {
+            line.px = 0.f; line.py = 0.f;
+            const float inv = 1.0f / sqrtf(dot2(-rp1y, rp1x, -rp1y, rp1x));
+            line.dx = -rp1y * inv; line.dy = rp1x * inv;
+            return true;
+        }
+        return false;
+    } else if (s > 1.0f && distSq2 <= radiusSq) {
+        if (o2.convex && det2(rp2x, rp2y, o2.ux, o2.uy) >= 0.0f) {
+            line.px = 0.f; line.py = 0.f;
+            const float inv = 1.0f / sqrtf(dot2(-rp2y, rp2x, -rp2y, rp2x));
+            line.dx = -rp2y * inv; line.dy = rp2x * inv;
+            return true;
+        }
+        return false;
+    } else if (s >= 0.0f && s < 1.0f && distSqLine <= radiusSq) {
+        line.px = 0.f; line.py = 0.f; line.dx = -o1.ux; line.dy = -o1.uy;
+        return true;
+    }
+
+    float llx, lly, rlx, rly; // left / right leg directions
+    if (s < 0.0f && distSqLine <= radiusSq) {
+        if (!o1.convex) return false;
+        o2 = o1; o2i = o1i;
+        const float leg1 = sqrtf(distSq1 - radiusSq);
+        const float inv = 1.0f / distSq1;
+        llx = (rp1x * leg1 - rp1y * radius) * inv; lly = (rp1x * radius + rp1y * leg1) * inv;
+        rlx = (rp1x * leg1 + rp1y * radius) * inv; rly = (-rp1x * radius + rp1y * leg1) * inv;
+    } else if (s > 1.0f && distSqLine <= radiusSq) {
+        if (!o2.convex) return false;
+        o1 = o2; o1i = o2i;
+        const float leg2 = sqrtf(distSq2 - radiusSq);
+        const float inv = 1.0f / distSq2;
+        llx = (rp2x * leg2 - rp2y * radius) * inv; lly = (rp2x * radius + rp2y * leg2) * inv;
+        rlx = (rp2x * leg2 + rp2y * radius) * inv; rly = (-rp2x * radius + rp2y * leg2) * inv;
+    } else {
+        if (o1.convex) {
+            const float leg1 = sqrtf(distSq1 - radiusSq);
+            const float inv = 1.0f / distSq1;
+            llx = (rp1x * leg1 - rp1y * radius) * inv; lly = (rp1x * radius + rp1y * leg1) * inv;
+        } else { llx = -o1.ux; lly = -o1.uy; }
+        if (o2.convex) {
+            const float leg2 = sqrtf(distSq2 - radiusSq);
+            const float inv = 1.0f / distSq2;
+            rlx = (rp2x * leg2 + rp2y * radius) * inv; rly = (-rp2x * radius + rp2y * leg2) * inv;
+        } else { rlx = o1.ux; rly = o1.uy; }
+    }
+
+    const ObstVert leftNeighbor = verts[o1.prev];
+    bool isLeftLegForeign = false, isRightLegForeign = false;
+    if (o1.convex && det2(llx, lly, -leftNeighbor.ux, -leftNeighbor.uy) >= 0.0f) {
+        llx = -leftNeighbor.ux; lly = -leftNeighbor.uy; isLeftLegForeign = true;
+    }
+    if (o2.convex && det2(rlx, rly, o2.ux, o2.uy) <= 0.0f) {
+        rlx = o2.ux; rly = o2.uy; isRightLegForeign = true;
+    }
+
+    const float lcx = invT * (o1.px - px), lcy = invT * (o1.py - py);
+    const float rcx = invT * (o2.px - px), rcy = invT * (o2.py - py);
+    const float cvx = rcx - lcx, cvy = rcy - lcy;
+    const bool same = (o1i == o2i);
+    const float t = same ? 0.5f : dot2(vx - lcx, vy - lcy, cvx, cvy) / dot2(cvx, cvy, cvx, cvy);
+    const float tLeft = dot2(vx - lcx, vy - lcy, llx, lly);
+    const float tRight = dot2(vx - rcx, vy - rcy, rlx, rly);
+    const float rs = radius * invT;
+
+    if ((t < 0.0f && tLeft < 0.0f) || (same && tLeft < 0.0f && tRight < 0.0f)) {
+        const float wx = vx - lcx, wy = vy - lcy;
+        const float inv = 1.0f / sqrtf(dot2(wx, wy, wx, wy));
+        const float unx = wx * inv, uny = wy * inv;
+        line.dx = uny; line.dy = -unx;
+        line.px = lcx + rs * unx; line.py = lcy + rs * uny;
+        return true;
+    } else if (t > 1.0f && tRight < 0.0f) {
+        const float wx = vx - rcx, wy = vy - rcy;
+        const float inv = 1.0f / sqrtf(dot2(wx, wy, wx, wy));
+        const float unx = wx * inv, uny = wy * inv;
+        line.dx = uny; line.dy = -unx;
+        line.px = rcx + rs * unx; line.py = rcy + rs * uny;
+        return true;
+    }
+
+    float distSqCutoff, distSqLeft, distSqRight;
+    if (t < 0.0f || t > 1.0f || same) distSqCutoff = INFINITY;
+    else { const float ax = vx - (lcx + t * cvx), ay = vy - (lcy + t * cvy); distSqCutoff = dot2(ax, ay, ax, ay); }
+    if (tLeft < 0.0f) distSqLeft = INFINITY;
+    else { const float ax = vx - (lcx + tLeft * llx), ay = vy - (lcy + tLeft * lly); distSqLeft = dot2(ax, ay, ax, ay); }
+    if (tRight < 0.0f) distSqRight = INFINITY;
+    else { const float ax = vx - (rcx + tRight * rlx), ay = vy - (rcy + tRight * rly); distSqRight = dot2(ax, ay, ax, ay); }
+
+    if (distSqCutoff <= distSqLeft && distSqCutoff <= distSqRight) {
+        line.dx = -o1.ux; line.dy = -o1.uy;
+        line.px = lcx + rs * (-line.dy); line.py = lcy + rs * line.dx;
+        return true;
+    } else if (distSqLeft <= distSqRight) {
+        if (isLeftLegForeign) return false;
+        line.dx = llx; line.dy = lly;
+        line.px = lcx + rs * (-line.dy); line.py = lcy + rs * line.dx;
+        return true;
+    } else {
+        if (isRightLegForeign) return false;
+        line.dx = -rlx; line.dy = -rly;
+        line.px = rcx + rs * (-line.dy); line.py = rcy + rs * line.dx;
+        return true;
+    }
+}
+
+// distSqPointLineSegment (RVO2 Definitions / Vector2.h)
+__device__ float dist_sq_point_segment(float ax, float ay, float bx, float by, float cx, float cy)
+{
+    const float r = dot2(cx - ax, cy - ay, bx - ax, by - ay) / dot2(bx - ax, by - ay, bx - ax, by - ay);
+    if (r < 0.0f) return dot2(cx - ax, cy - ay, cx - ax, cy - ay);
+    if (r > 1.0f) return dot2(cx - bx, cy - by, cx - bx, cy - by);
+    const float qx = cx - (ax + r * (bx - ax)), qy = cy - (ay + r * (by - ay));
+    return dot2(qx, qy, qx, qy);
+}
+
+// KdTree::queryObstacleTreeRecursive + Agent::insertObstacleNeighbor, iterative, run by ONE lane.
+// ids/ds = per-warp shared scratch (SNB_MAX_ORCA_LINES entries).  Returns the neighbour count (-1 on overflow).
+__device__ int obstacle_neighbors(const ObstVert *verts, const BspNode *nodes, int root, float px, float py, float rangeSq,
+                                  int *ids, float *ds)
+{
+    int cnt = 0;
+    int stack_node[48];
+    unsigned char stack_stage[48];
+    int sp = 0;
+    if (root < 0) return 0;
+    stack_node[0] = root; stack_stage[0] = 0; sp = 1;
+    while (sp > 0) {
+        const int node = stack_node[sp - 1];
+        const int stage = stack_stage[sp - 1];
+        const BspNode nd = nodes[node];
+        const ObstVert o1 = verts[nd.obstacle];
+        const ObstVert o2 = verts[o1.next];
+        // leftOf(o1, o2, p) = det(o1 - p, o2 - o1)
+        const float agentLeftOfLine = det2(o1.px - px, o1.py - py, o2.px - o1.px, o2.py - o1.py);
+        if (stage == 0) {
+            stack_stage[sp - 1] = 1;
+            const int first = (agentLeftOfLine >= 0.0f ? nd.left : nd.right);
+            if (first >= 0) { if (sp >= 48) return -1; stack_node[sp] = first; stack_stage[sp] = 0; ++sp; }
+            continue;
+        }
+        --sp; // stage 1: this node, then maybe the far side
+        const float ex = o2.px - o1.px, ey = o2.py - o1.py;
+        const float distSqLine = agentLeftOfLine * agentLeftOfLine / dot2(ex, ey, ex, ey);
+        if (distSqLine < rangeSq) {
+            if (agentLeftOfLine < 0.0f) {
+                const float distSq = dist_sq_point_segment(o1.px, o1.py, o2.px, o2.py, px, py);
+                if (distSq < rangeSq) {
+                    if (cnt >= SNB_MAX_ORCA_LINES) return -1;
+                    int i = cnt++;
+                    while (i != 0 && distSq < ds[i - 1]) { ds[i] = ds[i - 1]; ids[i] = ids[i - 1]; --i; }
+                    ds[i] = distSq; ids[i] = nd.obstacle;
+                }
+            }
+            const int other = (agentLeftOfLine >= 0.0f ? nd.right : nd.left);
+            if (other >= 0) { if (sp >= 48) return -1; stack_node[sp] = other; stack_stage[sp] = 0; ++sp; }
+        }
+    }
+    return cnt;
+}
+
+// KdTree::buildAgentTree + an unpruned queryAgentTreeRecursive from agent 0: writes, for every agent
+// k of the throw-away simulator (0 = self, 1.. = `ob` order), its position in the visit sequence.  Only needed to
+// order EXACTLY equidistant neighbours when the simulator has more than MAX_LEAF_SIZE=10 agents; run by one lane.
+__device__ void kd_visit_rank(int n, const float *ax, const float *ay, unsigned char *vrank)
+{
+    unsigned char idx[SNB_MAX_AGENTS_PER_ENV + 1];
+    struct Node { unsigned char begin, end, left, right; float minX, maxX, minY, maxY; };
+    Node tree[2 * (SNB_MAX_AGENTS_PER_ENV + 1)];
+    for (int i = 0; i < n; ++i) idx[i] = (unsigned char)i;
+    // build (pre-order, explicit stack)
+    unsigned char sb[40], se[40], sn[40];
+    int sp = 0;
+    sb[0] = 0; se[0] = (unsigned char)n; sn[0] = 0; sp = 1;
+    while (sp > 0) {
+        --sp;
+        const int begin = sb[sp], end = se[sp], node = sn[sp];
+        Node &t = tree[node];
+        t.begin = (unsigned char)begin; t.end = (unsigned char)end; t.left = t.right = 0;
+        t.minX = t.maxX = ax[idx[begin]]; t.minY = t.maxY = ay[idx[begin]];
+        for (int i = begin + 1; i < end; ++i) {
+            t.maxX = fmaxf(t.maxX, ax[idx[i]]); t.minX = fminf(t.minX, ax[idx[i]]);
+            t.maxY = fmaxf(t.maxY, ay[idx[i]]); t.minY = fminf(t.minY, ay[idx[i]]);
+        }
+        if (end - begin > 10) {
+            const bool isVertical = (t.maxX - t.minX > t.maxY - t.minY);
+            const float splitValue = isVertical ? 0.5f * (t.maxX + t.minX) : 0.5f * (t.maxY + t.minY);
+            int left = begin, right = end;
+            while (left < right) {
+                while (left < right && (isVertical ? ax[idx[left]] : ay[idx[left]]) < splitValue) ++left;
+                while (right > left && (isVertical ? ax[idx[right - 1]] : ay[idx[right - 1]]) >= splitValue) --right;
+                if (left < right) { const unsigned char tmp = idx[left]; idx[left] = idx[right - 1]; idx[right - 1] = tmp; ++left; --right; }
+            }
+            if (left == begin) { ++left; ++right; }
+            t.left = (unsigned char)(node + 1);
+            t.right = (unsigned char)(node + 2 * (left - begin));
+            // push right first so that left is built first (order is irrelevant for the result)
+            sb[sp] = (unsigned char)left; se[sp] = (unsigned char)end; sn[sp] = t.right; ++sp;
+            sb[sp] = (unsigned char)begin; se[sp] = (unsigned char)left; sn[sp] = t.left; ++sp;
+        }
+    }
+    // query from agent 0 without pruning: nearer child first (strict <), see queryAgentTreeRecursive
+    const float qx = ax[0], qy = ay[0];
+    int pos = 0;
+    sn[0] = 0; sp = 1;
+    while (sp > 0) {
+        const int node = sn[--sp];
+        const Node &t = tree[node];
+        if (t.end - t.begin <= 10) {
+            for (int i = t.begin; i < t.end; ++i) vrank[idx[i]] = (unsigned char)pos++;
+        } else {
+            const Node &L = tree[t.left], &R = tree[t.right];
+            float a, b, c, d;
+            a = fmaxf(0.0f, L.minX - qx); b = fmaxf(0.0f, qx - L.maxX); c = fmaxf(0.0f, L.minY - qy); d = fmaxf(0.0f, qy - L.maxY);
+            const float distSqLeft = a * a + b * b + c * c + d * d;
+            a = fmaxf(0.0f, R.minX - qx); b = fmaxf(0.0f, qx - R.maxX); c = fmaxf(0.0f, R.minY - qy); d = fmaxf(0.0f, qy - R.maxY);
+            const float distSqRight = a * a + b * b + c * c + d * d;
+            if (distSqLeft < distSqRight) { sn[sp++] = t.right; sn[sp++] = t.left; }
+            else { sn[sp++] = t.left; sn[sp++] = t.right; }
+        }
+    }
+}
+
+// per-warp shared scratch
+struct WarpScratch {
+    Line lines[SNB_MAX_ORCA_LINES];
+    int nb[SNB_MAX_AGENTS_PER_ENV];
+    int obst_ids[SNB_MAX_ORCA_LINES];
+    float obst_ds[SNB_MAX_ORCA_LINES];
+    float ax[SNB_MAX_AGENTS_PER_ENV + 1], ay[SNB_MAX_AGENTS_PER_ENV + 1];
+    unsigned char vrank[SNB_MAX_AGENTS_PER_ENV + 4];
+};
+
+// shared-memory view of the CTA's environment tile (all fp64)
+struct Tile {
+    double *px, *py, *vx, *vy, *rad, *gx, *gy, *vpref; // [epc*H]
+    double *ex_px, *ex_py, *ex_vx, *ex_vy, *ex_rad;   // [epc*E]
+    double *act;                                        // [epc*H*2] human actions
+    double *segs;                                       // [n_seg*4]
+};
+
+// candidate c (0..n_others-1) of human i in local env e -> observable state (ob order: other humans, then extras)
+__device__ __forceinline__ void load_other(const Tile &T, int H, int E, int e, int i, int c, double &opx, double &opy,
+                                           double &ovx, double &ovy, double &orad, int &agent_id)
+{
+    if (c < H - 1) {
+        const int j = (c < i) ? c : c + 1;
+        const int k = e * H + j;
+        opx = T.px[k]; opy = T.py[k]; ovx = T.vx[k]; ovy = T.vy[k]; orad = T.rad[k];
+        agent_id = j;
+    } else {
+        const int x = c - (H - 1);
+        const int k = e * E + x;
+        opx = T.ex_px[k]; opy = T.ex_py[k]; ovx = T.ex_vx[k]; ovy = T.ex_vy[k]; orad = T.ex_rad[k];
+        agent_id = H + x;
+    }
+}
+
+// ORCA.predict / ORCAPlus.predict for one human, by one warp.  Returns the new velocity (warp-uniform).
+__device__ void orca_predict_warp(const CrowdParams &P, const Tile &T, WarpScratch &W, int e, int i, int lane, int genv,
+                                  float &out_vx, float &out_vy)
+{
+    const SnbPolicyCfg &cfg = P.cfg;
+    const int H = P.st.H, E = P.st.E;
+    const int n_others = H - 1 + P.st.n_obs_extras;
+    const int k = e * H + i;
+    const double dpx = T.px[k], dpy = T.py[k];
+    const float px = (float)dpx, py = (float)dpy, vx = (float)T.vx[k], vy = (float)T.vy[k];
+    const float radius = (float)(T.rad[k] + 0.01 + cfg.safety_space);   // orca.py:100
+    const float maxSpeed = (float)T.vpref[k];
+    const float neighborDist = (float)cfg.neighbor_dist;
+    const float timeHorizon = (float)cfg.time_horizon, timeHorizonObst = (float)cfg.time_horizon_obst;
+    const float timeStep = (float)cfg.time_step;
+    const int maxNeighbors = cfg.max_neighbors;
+
+    // preferred velocity in double, then narrowed (orca.py:113-123 / orca_plus.py:68-79)
+    const double dvx = T.gx[k] - dpx, dvy = T.gy[k] - dpy;
+    const double speed = sqrt(fma(dvy, dvy, dvx * dvx)); // np.linalg.norm: BLAS dot fuses
+    double pvx, pvy;
+    if (cfg.policy == SNB_POLICY_ORCA_PLUS) {
+        const double vp = T.vpref[k] - 1e-3;
+        if (speed > vp) { pvx = dvx / speed * vp; pvy = dvy / speed * vp; } else { pvx = dvx; pvy = dvy; }
+    } else {
+        if (speed > 1) { pvx = dvx / speed; pvy = dvy / speed; } else { pvx = dvx; pvy = dvy; }
+    }
+    const float prefx = (float)pvx, prefy = (float)pvy;
+
+    // ---- agent neighbours: lanes = candidates ----
+    float opx = 0.f, opy = 0.f, ovx = 0.f, ovy = 0.f, orad = 0.f;
+    int agent_id = -1;
+    bool in_range = false;
+    float distSq = INFINITY;
+    if (lane < n_others) {
+        double a, b, c, d, r;
+        load_other(T, H, E, e, i, lane, a, b, c, d, r, agent_id);
+        opx = (float)a; opy = (float)b; ovx = (float)c; ovy = (float)d;
+        orad = (float)(r + 0.01 + cfg.safety_space);
+        const float ddx = px - opx, ddy = py - opy;
+        distSq = dot2(ddx, ddy, ddx, ddy);
+        in_range = (maxNeighbors > 0) && (distSq < neighborDist * neighborDist);
+    }
+    int rank = 0;
+    bool tie = false;
+    for (int j = 0; j < n_others; ++j) {
+        const float dj = __shfl_sync(FULL, distSq, j);
+        const bool inj = __shfl_sync(FULL, (int)in_range, j) != 0;
+        if (inj && (dj < distSq || (dj == distSq && j < lane))) ++rank;
+        if (inj && in_range && j != lane && dj == distSq) tie = true;
+    }
+    if (__any_sync(FULL, tie) && n_others + 1 > 10) {
+        // exact distance tie in a simulator with a split kd-tree: order the tied agents by RVO2's visit sequence
+        if (lane == 0) { W.ax[0] = px; W.ay[0] = py; }
+        if (lane < n_others) { W.ax[lane + 1] = opx; W.ay[lane + 1] = opy; }
+        __syncwarp();
+        if (lane == 0) kd_visit_rank(n_others + 1, W.ax, W.ay, W.vrank);
+        __syncwarp();
+        const int myv = (lane < n_others) ? W.vrank[lane + 1] : 0;
+        rank = 0;
+        for (int j = 0; j < n_others; ++j) {
+            const float dj = __shfl_sync(FULL, distSq, j);
+            const bool inj = __shfl_sync(FULL, (int)in_range, j) != 0;
+            const int vj = __shfl_sync(FULL, myv, j);
+            if (inj && (dj < distSq || (dj == distSq && vj < myv))) ++rank;
+        }
+        __syncwarp();
+    }
+    const unsigned inmask = __ballot_sync(FULL, in_range);
+    const int n_in = __popc(inmask);
+    const int n_nb = n_in < maxNeighbors ? n_in : maxNeighbors;
+    if (in_range && rank < n_nb) W.nb[rank] = lane;
+    __syncwarp();
+    if (P.nbr_cnt && lane == 0) P.nbr_cnt[genv * H + i] = n_nb;
+
+    // ---- obstacle neighbours and lines (ORCAPlus only) ----
+    int numObstLines = 0;
+    bool overflow = false;
+    if (cfg.policy == SNB_POLICY_ORCA_PLUS && P.n_vert > 0) {
+        int n_on = 0;
+        if (lane == 0) {
+            const float rs = timeHorizonObst * maxSpeed + radius;
+            n_on = obstacle_neighbors(P.verts, P.nodes, P.bsp_root, px, py, rs * rs, W.obst_ids, W.obst_ds);
+        }
+        n_on = __shfl_sync(FULL, n_on, 0);
+        __syncwarp();
+        if (n_on < 0) { overflow = true; n_on = 0; }
+        const float invT = 1.0f / timeHorizonObst;
+        Line cand = Line{0.f, 0.f, 1.f, 0.f};
+        bool valid = false;
+        float r1x = 0.f, r1y = 0.f, r2x = 0.f, r2y = 0.f;
+        if (lane < n_on) {
+            const int o1 = W.obst_ids[lane];
+            const ObstVert a = P.verts[o1], b = P.verts[a.next];
+            r1x = a.px - px; r1y = a.py - py; r2x = b.px - px; r2y = b.py - py;
+            valid = obstacle_orca_line(P.verts, o1, px, py, vx, vy, radius, invT, cand);
+        }
+        // sequential "already covered" sweep (depends only on the lines accepted so far)
+        bool accepted = false;
+        for (int q = 0; q < n_on; ++q) {
+            const float q1x = __shfl_sync(FULL, r1x, q), q1y = __shfl_sync(FULL, r1y, q);
+            const float q2x = __shfl_sync(FULL, r2x, q), q2y = __shfl_sync(FULL, r2y, q);
+            bool covers = false;
+            if (accepted && lane < q) {
+                covers = (det2(invT * q1x - cand.px, invT * q1y - cand.py, cand.dx, cand.dy) - invT * radius >= -RVO_EPSILON) &&
+                         (det2(invT * q2x - cand.px, invT * q2y - cand.py, cand.dx, cand.dy) - invT * radius >= -RVO_EPSILON);
+            }
+            const bool covered = __any_sync(FULL, covers) != 0;
+            if (lane == q) accepted = valid && !covered;
+        }
+        const unsigned amask = __ballot_sync(FULL, accepted);
+        numObstLines = __popc(amask);
+        if (accepted) W.lines[__popc(amask & ((1u << lane) - 1u))] = cand;
+    }
+
+    // ---- agent lines: lane q builds the half-plane of neighbour q ----
+    int nLines = numObstLines + n_nb;
+    if (nLines > SNB_MAX_ORCA_LINES) { overflow = true; nLines = SNB_MAX_ORCA_LINES; }
+    {
+        const int src = (lane < n_nb) ? W.nb[lane] : 0;
+        const float qpx = __shfl_sync(FULL, opx, src), qpy = __shfl_sync(FULL, opy, src);
+        const float qvx = __shfl_sync(FULL, ovx, src), qvy = __shfl_sync(FULL, ovy, src);
+        const float qr = __shfl_sync(FULL, orad, src);
+        const int qid = __shfl_sync(FULL, agent_id, src);
+        if (lane < n_nb && numObstLines + lane < SNB_MAX_ORCA_LINES)
+            W.lines[numObstLines + lane] = agent_orca_line(px, py, vx, vy, radius, qpx, qpy, qvx, qvy, qr, 1.0f / timeHorizon, timeStep);
+        if (P.nbr && lane < maxNeighbors) P.nbr[(size_t)(genv * H + i) * maxNeighbors + lane] = (lane < n_nb) ? qid : -1;
+    }
+    __syncwarp();
+    const Line my = (lane < nLines) ? W.lines[lane] : Line{0.f, 0.f, 1.f, 0.f};
+    __syncwarp();
+    if (overflow && lane == 0 && P.status) atomicExch(P.status, SNB_EOVERFLOW);
+
+    float rx, ry;
+    const int lineFail = lp2_warp(my, nLines, maxSpeed, prefx, prefy, false, rx, ry, lane);
+    if (lineFail < nLines) lp3_warp(my, nLines, numObstLines, lineFail, maxSpeed, rx, ry, lane, W.lines);
+    out_vx = rx; out_vy = ry;
+}
+
+// utils_plus.closest_point_on_segment (utils_plus.py:21-42)
+__device__ __forceinline__ void closest_point_on_segment(double x1, double y1, double x2, double y2, double x3, double y3,
+                                                         double &ox, double &oy)
+{
+    const double px = x2 - x1, py = y2 - y1;
+    if (px == 0 && py == 0) { ox = x1; oy = y1; return; } // quirk q12: unreachable with valid layouts
+    double u = ((x3 - x1) * px + (y3 - y1) * py) / (px * px + py * py);
+    if (u > 1) u = 1; else if (u < 0) u = 0;
+    ox = x1 + u * px; oy = y1 + u * py;
+}
+
+// SFM.predict for one human, by one warp (social_force.py:38-94).  fp64 like the reference; the pairwise and wall
+// forces are summed with a shuffle reduction (summation order differs from the reference's sequential += by
+// rounding only; tolerance stated in the tests).
+__device__ void sfm_predict_warp(const CrowdParams &P, const Tile &T, int e, int i, int lane, double &out_vx, double &out_vy)
+{
+    const SnbPolicyCfg &cfg = P.cfg;
+    const int H = P.st.H, E = P.st.E;
+    const int n_others = H - 1 + P.st.n_obs_extras;
+    const int k = e * H + i;
+    const double px = T.px[k], py = T.py[k], vx = T.vx[k], vy = T.vy[k], radius = T.rad[k];
+    const double gx = T.gx[k], gy = T.gy[k], v_pref = T.vpref[k];
+    double fx = 0.0, fy = 0.0;
+    for (int c = lane; c < n_others + P.n_seg; c += 32) {
+        if (c < n_others) {
+            double opx, opy, ovx, ovy, orad; int id;
+            load_other(T, H, E, e, i, c, opx, opy, ovx, ovy, orad, id);
+            const double adjustment = fabs(cfg.sfm_radius - orad) + 0.01;
+            const double dx = px - opx, dy = py - opy;
+            const double d = sqrt(dx * dx + dy * dy);
+            const double ee = cfg.A * exp((radius + orad + adjustment - d) / cfg.B);
+            fx += ee * (dx / d); fy += ee * (dy / d);
+        } else {
+            const int s = c - n_others;
+            const double *L = T.segs + 4 * s;
+            double As, Bs;
+            if (cfg.is_bottleneck && s >= 2) { As = cfg.A_bottleneck; Bs = cfg.B_bottleneck; } else { As = cfg.A_static; Bs = cfg.B_static; }
+            double ox, oy;
+            closest_point_on_segment(L[0], L[1], L[2], L[3], px, py, ox, oy);
+            const double dx = px - ox, dy = py - oy;
+            const double d = sqrt(dx * dx + dy * dy);
+            const double ee = As * exp((radius + 0.01 - d) / Bs);
+            fx += ee * (dx / d); fy += ee * (dy / d);
+        }
+    }
+    fx = warp_sum(fx); fy = warp_sum(fy);
+    double ddx = gx - px, ddy = gy - py;
+    double dist_to_goal = sqrt(ddx * ddx + ddy * ddy);
+    dist_to_goal = dist_to_goal < 1e-6 ? 1.0 : dist_to_goal;
+    const double desired_vx = (ddx / dist_to_goal) * v_pref, desired_vy = (ddy / dist_to_goal) * v_pref;
+    const double cdx = cfg.KI * (desired_vx - vx), cdy = cfg.KI * (desired_vy - vy);
+    const double new_vx = vx + (cdx + fx) * cfg.time_step, new_vy = vy + (cdy + fy) * cfg.time_step;
+    const double act_norm = sqrt(fma(new_vy, new_vy, new_vx * new_vx)); // np.linalg.norm
+    if (act_norm > v_pref) { out_vx = new_vx / act_norm * v_pref; out_vy = new_vy / act_norm * v_pref; }
+    else { out_vx = new_vx; out_vy = new_vy; }
+}
+
+// ---- fp64 geometry of the clamp (numpy semantics: np.dot / np.linalg.norm fuse, see oracle/crowd_oracle.c) ----
+__device__ __forceinline__ double npdot2(double x0, double x1, double y0, double y1) { return fma(x1, y1, x0 * y0); }
+__device__ __forceinline__ double npnorm2(double x, double y) { return sqrt(fma(y, y, x * x)); }
+
+// utils_plus.closest_distance_between_line_segments (utils_plus.py:205-338), z = 0
+__device__ void segseg(const double *a0, const double *a1_in, const double *b0, const double *b1_in, double *pA, double *pB, double &dist)
+{
+    double a1[2] = {a1_in[0], a1_in[1]}, b1[2] = {b1_in[0], b1_in[1]};
+    double A[2] = {a1[0] - a0[0], a1[1] - a0[1]}, B[2] = {b1[0] - b0[0], b1[1] - b0[1]};
+    const double magA = npnorm2(A[0], A[1]), magB = npnorm2(B[0], B[1]);
+    double _A[2], _B[2];
+    if (magA < 1e-8) { a1[0] = a0[0]; a1[1] = a0[1]; _A[0] = _A[1] = 0.0; } else { _A[0] = A[0] / magA; _A[1] = A[1] / magA; }
+    if (magB < 1e-8) { b1[0] = b0[0]; b1[1] = b0[1]; _B[0] = _B[1] = 0.0; } else { _B[0] = B[0] / magB; _B[1] = B[1] / magB; }
+    const double cz = _A[0] * _B[1] - _A[1] * _B[0];
+    const double ncross = sqrt(cz * cz);
+    const double denom = ncross * ncross;
+#define SS_RET(PA, PB) do { pA[0] = (PA)[0]; pA[1] = (PA)[1]; pB[0] = (PB)[0]; pB[1] = (PB)[1]; \
+                            dist = npnorm2(pA[0] - pB[0], pA[1] - pB[1]); return; } while (0)
+    if (denom == 0.0) {
+        const double d0 = npdot2(_A[0], _A[1], b0[0] - a0[0], b0[1] - a0[1]);
+        const double d1 = npdot2(_A[0], _A[1], b1[0] - a0[0], b1[1] - a0[1]);
+        if (d0 <= 0 && 0 >= d1) {
+            if (fabs(d0) < fabs(d1)) SS_RET(a0, b0);
+            SS_RET(a0, b1);
+        } else if (d0 >= magA && magA <= d1) {
+            if (fabs(d0) < fabs(d1)) SS_RET(a1, b0);
+            SS_RET(a1, b1);
+        } else {
+            double a0f[2], _Af[2], qA[2], qB[2];
+            if (npnorm2(_A[0] - _B[0], _A[1] - _B[1]) < 1e-8 || magB < 1e-8) { a0f[0] = a0[0]; a0f[1] = a0[1]; _Af[0] = _A[0]; _Af[1] = _A[1]; }
+            else { a0f[0] = a1[0]; a0f[1] = a1[1]; _Af[0] = -_A[0]; _Af[1] = -_A[1]; }
+            const double d0f = npdot2(_Af[0], _Af[1], b0[0] - a0f[0], b0[1] - a0f[1]);
+            if (d0f >= 0) {
+                qB[0] = b0[0]; qB[1] = b0[1];
+                const double t = npdot2(_Af[0], _Af[1], qB[0] - a0f[0], qB[1] - a0f[1]);
+                qA[0] = a0f[0] + _Af[0] * t; qA[1] = a0f[1] + _Af[1] * t;
+            } else {
+                qA[0] = a0f[0]; qA[1] = a0f[1];
+                const double t = npdot2(_B[0], _B[1], qA[0] - b0[0], qA[1] - b0[1]);
+                qB[0] = b0[0] + _B[0] * t; qB[1] = b0[1] + _B[1] * t;
+            }
+            SS_RET(qA, qB);
+        }
+    }
+    const double t[2] = {b0[0] - a0[0], b0[1] - a0[1]};
+    const double detA = cz * (t[0] * _B[1] - t[1] * _B[0]);
+    const double detB = cz * (t[0] * _A[1] - t[1] * _A[0]);
+    const double t0 = detA / denom, t1 = detB / denom;
+    double qA[2] = {a0[0] + _A[0] * t0, a0[1] + _A[1] * t0}, qB[2] = {b0[0] + _B[0] * t1, b0[1] + _B[1] * t1};
+    if (t0 < 0) { qA[0] = a0[0]; qA[1] = a0[1]; } else if (t0 > magA) { qA[0] = a1[0]; qA[1] = a1[1]; }
+    if (t1 < 0) { qB[0] = b0[0]; qB[1] = b0[1]; } else if (t1 > magB) { qB[0] = b1[0]; qB[1] = b1[1]; }
+    if (t0 < 0 || t0 > magA) {
+        double dot = npdot2(_B[0], _B[1], qA[0] - b0[0], qA[1] - b0[1]);
+        if (dot < 0) dot = 0; else if (dot > magB) dot = magB;
+        qB[0] = b0[0] + _B[0] * dot; qB[1] = b0[1] + _B[1] * dot;
+    }
+    if (t1 < 0 || t1 > magB) {
+        double dot = npdot2(_A[0], _A[1], qB[0] - a0[0], qB[1] - a0[1]);
+        if (dot < 0) dot = 0; else if (dot > magA) dot = magA;
+        qA[0] = a0[0] + _A[0] * dot; qA[1] = a0[1] + _A[1] * dot;
+    }
+    SS_RET(qA, qB);
+#undef SS_RET
+}
+
+// Agent.compute_position (agent_plus.py:175-185)
+__device__ __forceinline__ void compute_position(double px, double py, double theta, int kin, double a0, double a1, double dt,
+                                                 double &ox, double &oy)
+{
+    if (kin == SNB_KIN_HOLONOMIC) { ox = px + a0 * dt; oy = py + a1 * dt; }
+    else { const double th = theta + a1; ox = px + cos(th) * a0 * dt; oy = py + sin(th) * a0 * dt; }
+}
+
+// CrowdSimPlus.constrain_agent_action_exact (crowd_sim_plus.py:869-989)
+__device__ void constrain_action(double px, double py, double theta, double r, double dt, int kin, double a0, double a1,
+                                 int n_seg, const double *segs, double &o0, double &o1)
+{
+    const double PI = 3.14159265358979323846;
+    const double cur[2] = {px, py};
+    double fut[2];
+    compute_position(px, py, theta, kin, a0, a1, dt, fut[0], fut[1]);
+    const double mdir[2] = {fut[0] - cur[0], fut[1] - cur[1]};
+    const double movement_mag = npnorm2(mdir[0], mdir[1]);
+    double f0 = a0, f1 = a1;
+    for (int k = 0; k < n_seg; ++k) {
+        const double *L = segs + 4 * k;
+        double pA[2], pB[2], closest_distance;
+        segseg(L, L + 2, cur, fut, pA, pB, closest_distance);
+        if (!(closest_distance - r < 0.0)) continue;
+        double fin[2];
+        if ((npnorm2(pA[0] - L[0], pA[1] - L[1]) < 1e-8 || npnorm2(pA[0] - L[2], pA[1] - L[3]) < 1e-8) &&
+            npnorm2(pA[0] - pB[0], pA[1] - pB[1]) > 1e-8) {
+            const double dvec[2] = {pB[0] - cur[0], pB[1] - cur[1]};
+            const double dir_mag = npnorm2(dvec[0], dvec[1]);
+            double _d[2], redux;
+            if (dir_mag > 0.0 && npnorm2(pA[0] - cur[0], pA[1] - cur[1]) - r < 1e-4 &&
+                npdot2(mdir[0], mdir[1], pA[0] - cur[0], pA[1] - cur[1]) > -1e-8) {
+                _d[0] = dvec[0] / dir_mag; _d[1] = dvec[1] / dir_mag; redux = dir_mag;
+            } else if (dir_mag > 0.0) {
+                _d[0] = dvec[0] / dir_mag; _d[1] = dvec[1] / dir_mag;
+                const double av = npdot2(-dvec[0], -dvec[1], pA[0] - pB[0], pA[1] - pB[1]) / (dir_mag * closest_distance);
+                const double clipped = av < -1.0 ? -1.0 : (av > 1.0 ? 1.0 : av);
+                const double alpha = acos(clipped);
+                if (alpha == PI) redux = r - closest_distance;
+                else {
+                    const double gamma = asin(closest_distance * sin(alpha) / r);
+                    const double beta = PI - alpha - gamma;
+                    redux = r * sin(beta) / sin(alpha) + 1e-7;
+                }
+            } else { redux = 0.0; _d[0] = dvec[0]; _d[1] = dvec[1]; }
+            const double m = (dir_mag - redux) > 0 ? (dir_mag - redux) : 0;
+            fin[0] = cur[0] + _d[0] * m; fin[1] = cur[1] + _d[1] * m;
+        } else {
+            // closest_point_on_segment_extended (utils_plus.py:44-65)
+            double cl[2];
+            {
+                const double sx = L[2] - L[0], sy = L[3] - L[1];
+                if (sx == 0 && sy == 0) { cl[0] = L[0]; cl[1] = L[1]; }
+                else { const double u = ((cur[0] - L[0]) * sx + (cur[1] - L[1]) * sy) / (sx * sx + sy * sy); cl[0] = L[0] + u * sx; cl[1] = L[1] + u * sy; }
+            }
+            if (movement_mag > 0.0 && npnorm2(cl[0] - cur[0], cl[1] - cur[1]) - r < 1e-4 &&
+                npdot2(mdir[0], mdir[1], cl[0] - cur[0], cl[1] - cur[1]) > -1e-8) {
+                fin[0] = cur[0]; fin[1] = cur[1];
+            } else if (movement_mag > 0.0) {
+                // intersection_of_vec_line_and_2p_line (utils_plus.py:6-18)
+                const double x1 = L[0], y1 = L[1], x2 = L[2], y2 = L[3];
+                const double x3 = cur[0], y3 = cur[1], x4 = cur[0] + mdir[0], y4 = cur[1] + mdir[1];
+                const double den = (x1 - x2) * (y3 - y4) - (y1 - y2) * (x3 - x4);
+                const double ix = ((x1 * y2 - y1 * x2) * (x3 - x4) - (x1 - x2) * (x3 * y4 - y3 * x4)) / den;
+                const double iy = ((x1 * y2 - y1 * x2) * (y3 - y4) - (y1 - y2) * (x3 * y4 - y3 * x4)) / den;
+                const double dc_0 = sqrt((cur[0] - cl[0]) * (cur[0] - cl[0]) + (cur[1] - cl[1]) * (cur[1] - cl[1]));
+                double des = (dc_0 - (r + 1e-7)) / dc_0;
+                if (!(des > 0.0)) des = 0.0;
+                fin[0] = cur[0] + (ix - cur[0]) * des; fin[1] = cur[1] + (iy - cur[1]) * des;
+            } else { fin[0] = cur[0]; fin[1] = cur[1]; }
+        }
+        if (kin == SNB_KIN_HOLONOMIC) {
+            const double v_x = (fin[0] - cur[0]) / dt, v_y = (fin[1] - cur[1]) / dt;
+            if ((v_x * v_x + v_y * v_y) < (f0 * f0 + f1 * f1)) { f0 = v_x; f1 = v_y; }
+        } else {
+            if (a0 > 0) { const double v = npnorm2(fin[0] - cur[0], fin[1] - cur[1]) / dt; if (v < f0) { f0 = v; f1 = a1; } }
+            else { const double v = -npnorm2(fin[0] - cur[0], fin[1] - cur[1]) / dt; if (v > f0) { f0 = v; f1 = a1; } }
+        }
+    }
+    o0 = f0; o1 = f1;
+}
+
+// Human.get_g_xy (human_plus.py:19-52)
+__device__ __forceinline__ void get_g_xy(const SnbDoorCfg &door, double px, double py, double fgx, double fgy, double &gx, double &gy)
+{
+    if (door.enabled) {
+        const double ymin = py < fgy ? py : fgy, ymax = py > fgy ? py : fgy;
+        if (ymin < door.door_y_mid_min && ymax > door.door_y_mid_max) {
+            const double igx = door.door_x_mid, igy = 0.5 * (door.door_y_min + door.door_y_max);
+            const double vec_norm = npnorm2(igx - px, igy - py);
+            if (vec_norm <= door.door_width / 2.0) { gx = fgx; gy = fgy; } else { gx = igx; gy = igy; }
+            return;
+        }
+    }
+    gx = fgx; gy = fgy;
+}
+
+__device__ __forceinline__ double py_mod(double x, double y)
+{
+    double m = fmod(x, y);
+    if (m != 0.0 && ((m < 0) != (y < 0))) m += y;
+    return m;
+}
+
+// ---- TMA 1-D bulk copy + mbarrier (sm_90+/sm_100a) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+#define CROWD_THREADS 256
+
+__global__ void __launch_bounds__(CROWD_THREADS) crowd_step_kernel(const CrowdParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int H = P.st.H, E = P.st.E, B = P.st.B;
+    const int epc = P.epc;
+    const int env0 = blockIdx.x * epc;
+    const int nenv = min(epc, B - env0);
+    if (nenv <= 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int EA = ((epc * H + 1) & ~1); // padded to keep every array 16-byte aligned
+    const int EX = ((epc * (E > 0 ? E : 1) + 1) & ~1);
+
+    // carve shared memory
+    double *sd = reinterpret_cast<double *>(smem_raw);
+    Tile T;
+    T.px = sd; sd += EA; T.py = sd; sd += EA; T.vx = sd; sd += EA; T.vy = sd; sd += EA;
+    T.rad = sd; sd += EA; T.gx = sd; sd += EA; T.gy = sd; sd += EA; T.vpref = sd; sd += EA;
+    T.ex_px = sd; sd += EX; T.ex_py = sd; sd += EX; T.ex_vx = sd; sd += EX; T.ex_vy = sd; sd += EX; T.ex_rad = sd; sd += EX;
+    T.act = sd; sd += 2 * EA;
+    T.segs = sd; sd += 4 * ((P.n_seg + 1) & ~1);
+    double *s_next = sd; sd += 2 * EA;       // constrained human next positions
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sd); sd += 2;
+    WarpScratch *WS = reinterpret_cast<WarpScratch *>(sd);
+
+    // ---- stage the tile: 8 human arrays by TMA bulk copy when 16-byte aligned, else by plain loads ----
+    const int nA = nenv * H;
+    const size_t goff = (size_t)env0 * H;
+    const uint32_t bytes = (uint32_t)(nA * sizeof(double));
+    const double *src[8] = {P.st.px + goff, P.st.py + goff, P.st.vx + goff, P.st.vy + goff,
+                            P.st.radius + goff, P.st.gx + goff, P.st.gy + goff, P.st.vpref + goff};
+    double *dst[8] = {T.px, T.py, T.vx, T.vy, T.rad, T.gx, T.gy, T.vpref};
+    bool aligned = (bytes % 16u) == 0;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) aligned = aligned && ((reinterpret_cast<uintptr_t>(src[a]) & 15u) == 0);
+    if (aligned) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(bar, 8u * bytes);
+#pragma unroll
+            for (int a = 0; a < 8; ++a) tma_bulk_g2s(dst[a], src[a], bytes, bar);
+        }
+    } else {
+        for (int a = 0; a < 8; ++a)
+            for (int k = tid; k < nA; k += blockDim.x) dst[a][k] = src[a][k];
+    }
+    // extras + segments: small, plain (read-only path) loads overlap the bulk copies
+    for (int k = tid; k < nenv * E; k += blockDim.x) {
+        const size_t g = (size_t)env0 * E + k;
+        T.ex_px[k] = P.st.ex_px[g]; T.ex_py[k] = P.st.ex_py[g]; T.ex_vx[k] = P.st.ex_vx[g]; T.ex_vy[k] = P.st.ex_vy[g];
+        T.ex_rad[k] = P.st.ex_radius[g];
+    }
+    for (int k = tid; k < 4 * P.n_seg; k += blockDim.x) T.segs[k] = P.segs[k];
+    if (aligned) mbar_wait(bar, 0);
+    __syncthreads();
+
+    // ---- phase 1: one warp per human ----
+    for (int task = warp; task < nA; task += nwarps) {
+        const int e = task / H, i = task - e * H;
+        const int genv = env0 + e;
+        if (P.active && !P.active[genv]) continue;
+        double ax, ay;
+        if (P.cfg.policy == SNB_POLICY_SFM) {
+            sfm_predict_warp(P, T, e, i, lane, ax, ay);
+            if (P.nbr_cnt && lane == 0) P.nbr_cnt[genv * H + i] = 0;
+        } else {
+            float fx, fy;
+            orca_predict_warp(P, T, WS[warp], e, i, lane, genv, fx, fy);
+            ax = (double)fx; ay = (double)fy;
+        }
+        if (lane == 0) {
+            T.act[2 * task] = ax; T.act[2 * task + 1] = ay;
+            if (!P.full_step && P.out_v) { P.out_v[2 * (goff + task)] = ax; P.out_v[2 * (goff + task) + 1] = ay; }
+        }
+    }
+    if (!P.full_step) return;
+    __syncthreads();
+
+    // ---- phase 2a: one thread per human: static-obstacle clamp, next position ----
+    const double dt = P.cfg.time_step;
+    for (int task = tid; task < nA; task += blockDim.x) {
+        const int e = task / H;
+        const int genv = env0 + e;
+        if (P.active && !P.active[genv]) continue;
+        double c0 = T.act[2 * task], c1 = T.act[2 * task + 1];
+        if (P.n_seg > 0) constrain_action(T.px[task], T.py[task], 0.0, T.rad[task], dt, SNB_KIN_HOLONOMIC, c0, c1, P.n_seg, T.segs, c0, c1);
+        T.act[2 * task] = c0; T.act[2 * task + 1] = c1;
+        s_next[2 * task] = T.px[task] + c0 * dt; s_next[2 * task + 1] = T.py[task] + c1 * dt;
+    }
+    __syncthreads();
+
+    // ---- phase 2b: one thread per environment: robot clamp, collision scan, reward, robot update, clocks ----
+    for (int e = tid; e < nenv; e += blockDim.x) {
+        const int genv = env0 + e;
+        if (P.active && !P.active[genv]) continue;
+        const double rpx = T.ex_px[e * E], rpy = T.ex_py[e * E], rrad = T.ex_rad[e * E];
+        const double rtheta = P.st.rtheta[genv];
+        const double ra0 = P.robot_action[2 * genv], ra1 = P.robot_action[2 * genv + 1];
+        const int kin = P.st.robot_kinematics;
+        double c0 = ra0, c1 = ra1;
+        if (P.n_seg > 0) constrain_action(rpx, rpy, rtheta, rrad, dt, kin, ra0, ra1, P.n_seg, T.segs, c0, c1);
+        const bool stat_collision = (ra0 != c0); // quirk q11: only the first component is compared
+        double rnx, rny;
+        compute_position(rpx, rpy, rtheta, kin, c0, c1, dt, rnx, rny);
+        double dmin = INFINITY;
+        bool collision = false;
+        for (int i = 0; i < H; ++i) {
+            const int k = e * H + i;
+            const double closest = npnorm2(rnx - s_next[2 * k], rny - s_next[2 * k + 1]);
+            if (closest < (rrad + T.rad[k])) { collision = true; break; }
+            else if (closest < dmin) dmin = closest;
+        }
+        bool frozen;
+        if (kin == SNB_KIN_HOLONOMIC) frozen = sqrt(c0 * c0 + c1 * c1) * dt < 0.01;
+        else frozen = fabs(c0 * dt) < 0.01;
+        const double rgx = P.st.rgx[genv], rgy = P.st.rgy[genv];
+        const bool reached = npnorm2(rnx - rgx, rny - rgy) < rrad;
+        const double curr_dist = npnorm2(rgx - rnx, rgy - rny);
+        const double gt = P.st.global_time[genv];
+        double rew = 0.0;
+        int f = 0;
+        if (reached) { rew += P.rcfg.success_reward; f |= SNB_F_REACHED | SNB_F_DONE; }
+        else if (gt >= P.rcfg.time_limit) { rew += P.rcfg.timeout; f |= SNB_F_TIMEOUT | SNB_F_DONE; }
+        if (collision) { rew += P.rcfg.collision_penalty; f |= SNB_F_COLLISION; }
+        if (stat_collision) { rew += P.rcfg.wall_collision_penalty; f |= SNB_F_WALL; }
+        if (P.rcfg.discomfort && dmin < P.rcfg.discomfort_dist) {
+            rew += (dmin - P.rcfg.discomfort_dist) * P.rcfg.discomfort_penalty_factor * dt;
+            f |= SNB_F_DANGER;
+        }
+        if (P.rcfg.has_progress) {
+            rew += (P.st.prev_dist[genv] - curr_dist) * P.rcfg.progress_factor;
+            P.st.prev_dist[genv] = curr_dist;
+        }
+        if (frozen) { rew += P.rcfg.freezing_penalty; f |= SNB_F_FROZEN; }
+        if (P.reward) P.reward[genv] = rew;
+        if (P.dmin) P.dmin[genv] = dmin;
+        if (P.flags) P.flags[genv] = f;
+        // Agent.step for the robot (agent_plus.py:199-214)
+        const size_t gx = (size_t)genv * E;
+        P.st.ex_px[gx] = rnx; P.st.ex_py[gx] = rny;
+        if (kin == SNB_KIN_HOLONOMIC) {
+            P.st.ex_vx[gx] = c0; P.st.ex_vy[gx] = c1;
+            P.st.rtheta[genv] = atan2(c1, c0);
+        } else {
+            const double PI = 3.14159265358979323846;
+            const double un = py_mod(rtheta + c1, 2 * PI);
+            const double th = un > PI ? un - 2 * PI : un;
+            P.st.rtheta[genv] = th;
+            P.st.ex_vx[gx] = c0 * cos(th); P.st.ex_vy[gx] = c0 * sin(th);
+        }
+        P.st.global_time[genv] = gt + dt;
+    }
+
+    // ---- phase 2c: one thread per human: integrate, goal switch, arrival time; coalesced write-back ----
+    for (int task = tid; task < nA; task += blockDim.x) {
+        const int e = task / H;
+        const int genv = env0 + e;
+        if (P.active && !P.active[genv]) continue;
+        const size_t g = goff + task;
+        const double c0 = T.act[2 * task], c1 = T.act[2 * task + 1];
+        const double nx = s_next[2 * task], ny = s_next[2 * task + 1];
+        P.st.px[g] = nx; P.st.py[g] = ny; P.st.vx[g] = c0; P.st.vy[g] = c1;
+        P.st.theta[g] = atan2(c1, c0);
+        double ngx, ngy;
+        get_g_xy(P.door, nx, ny, P.st.fgx[g], P.st.fgy[g], ngx, ngy);
+        P.st.gx[g] = ngx; P.st.gy[g] = ngy;
+    }
+    __syncthreads(); // phase 2b's global_time stores are visible to the CTA after this barrier
+    for (int task = tid; task < nA; task += blockDim.x) {
+        const int e = task / H;
+        const int genv = env0 + e;
+        if (P.active && !P.active[genv]) continue;
+        const size_t g = goff + task;
+        if (P.st.human_time[g] == 0 &&
+            npnorm2(P.st.px[g] - P.st.gx[g], P.st.py[g] - P.st.gy[g]) < T.rad[task])
+            P.st.human_time[g] = P.st.global_time[genv];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------------------
+static int choose_epc(int H)
+{
+    int epc = 48 / (H > 0 ? H : 1);
+    if (epc < 1) epc = 1;
+    if (epc > 16) epc = 16;
+    if ((epc * H) & 1) epc += (epc > 1 ? -1 : 1); // keep epc*H even so that every tile offset is 16-byte aligned
+    if ((epc * H) & 1) epc = 2;
+    return epc;
+}
+
+static size_t crowd_smem_bytes(int epc, int H, int E, int n_seg)
+{
+    const size_t EA = (size_t)((epc * H + 1) & ~1);
+    const size_t EX = (size_t)((epc * (E > 0 ? E : 1) + 1) & ~1);
+    size_t d = 8 * EA + 5 * EX + 2 * EA + 4 * (size_t)((n_seg + 1) & ~1) + 2 * EA + 2;
+    return d * sizeof(double) + sizeof(WarpScratch) * (CROWD_THREADS / 32) + 16;
+}
+
+static int launch_crowd(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const SnbRewardCfg *rcfg, const SnbCrowdState *st,
+                        const SnbObstacles *obs, const double *robot_action, const uint8_t *active, double *reward,
+                        double *dmin, int *flags, double *out_v, int *nbr, int *nbr_cnt, int *status, int full_step, void *stream)
+{
+    SNB_REQUIRE(cfg && st, SNB_EINVAL, "crowd step: cfg/state is NULL");
+    SNB_REQUIRE(st->B >= 0 && st->H >= 1 && st->E >= 0, SNB_EINVAL, "crowd step: bad sizes B=%d H=%d E=%d", st->B, st->H, st->E);
+    SNB_REQUIRE(st->n_obs_extras >= 0 && st->n_obs_extras <= st->E, SNB_EINVAL, "crowd step: n_obs_extras=%d > E=%d", st->n_obs_extras, st->E);
+    SNB_REQUIRE(st->H - 1 + st->n_obs_extras <= SNB_MAX_AGENTS_PER_ENV, SNB_EUNSUPPORTED,
+                "crowd step: %d observed agents per human exceed SNB_MAX_AGENTS_PER_ENV=%d", st->H - 1 + st->n_obs_extras, SNB_MAX_AGENTS_PER_ENV);
+    SNB_REQUIRE(cfg->policy >= SNB_POLICY_ORCA && cfg->policy <= SNB_POLICY_SFM, SNB_EINVAL, "crowd step: unknown policy %d", cfg->policy);
+    SNB_REQUIRE(cfg->max_neighbors >= 0 && cfg->max_neighbors <= SNB_MAX_AGENTS_PER_ENV, SNB_EUNSUPPORTED, "crowd step: max_neighbors=%d unsupported", cfg->max_neighbors);
+    SNB_REQUIRE(st->px && st->py && st->vx && st->vy && st->gx && st->gy && st->vpref && st->radius, SNB_EINVAL, "crowd step: NULL human array");
+    SNB_REQUIRE(st->E == 0 || (st->ex_px && st->ex_py && st->ex_vx && st->ex_vy && st->ex_radius), SNB_EINVAL, "crowd step: NULL extras array");
+    if (full_step) {
+        SNB_REQUIRE(door && rcfg && robot_action, SNB_EINVAL, "env step: door/reward/robot_action is NULL");
+        SNB_REQUIRE(st->E >= 1, SNB_EINVAL, "env step: the robot must be extra 0 (E >= 1)");
+        SNB_REQUIRE(st->theta && st->fgx && st->fgy && st->human_time && st->rtheta && st->rgx && st->rgy && st->global_time,
+                    SNB_EINVAL, "env step: NULL state array");
+        SNB_REQUIRE(!rcfg->has_progress || st->prev_dist, SNB_EINVAL, "env step: prev_dist is NULL");
+    } else {
+        SNB_REQUIRE(out_v, SNB_EINVAL, "policy step: out_v is NULL");
+    }
+    if (st->B == 0) return SNB_OK;
+
+    CrowdParams P;
+    memset(&P, 0, sizeof(P));
+    P.cfg = *cfg;
+    if (door) P.door = *door;
+    if (rcfg) P.rcfg = *rcfg;
+    P.st = *st;
+    P.robot_action = robot_action; P.active = active; P.reward = reward; P.dmin = dmin; P.flags = flags;
+    P.out_v = out_v; P.nbr = nbr; P.nbr_cnt = nbr_cnt; P.status = status;
+    if (obs && obs->n_seg > 0) {
+        P.n_seg = obs->n_seg; P.segs = obs->d_segs;
+        P.n_vert = (int)obs->verts.size(); P.verts = obs->d_verts; P.nodes = obs->d_nodes; P.bsp_root = obs->root;
+    } else { P.bsp_root = -1; }
+    P.epc = choose_epc(st->H);
+    P.full_step = full_step;
+
+    const size_t smem = crowd_smem_bytes(P.epc, st->H, st->E, P.n_seg);
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(crowd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); });
+    SNB_CUDA_TRY(attr_err);
+    SNB_REQUIRE(smem <= 96 * 1024, SNB_EUNSUPPORTED, "crowd step: tile needs %zu B of shared memory", smem);
+    const int grid = (st->B + P.epc - 1) / P.epc;
+    crowd_step_kernel<<<grid, CROWD_THREADS, smem, (cudaStream_t)stream>>>(P);
+    snb_count_launch();
+    SNB_CUDA_TRY(cudaGetLastError());
+    return SNB_OK;
+}
+
+extern "C" int snb_policy_step(const SnbPolicyCfg *cfg, const SnbCrowdState *state, const SnbObstacles *obs, double *out_v_dev,
+                               int32_t *nbr_dev, int32_t *nbr_cnt_dev, int32_t *status_dev, void *stream)
+{
+    return launch_crowd(cfg, nullptr, nullptr, state, obs, nullptr, nullptr, nullptr, nullptr, nullptr, out_v_dev, nbr_dev,
+                        nbr_cnt_dev, status_dev, 0, stream);
+}
+
+extern "C" int snb_env_step(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const SnbRewardCfg *reward_cfg,
+                            const SnbCrowdState *state, const SnbObstacles *obs, const double *robot_action_dev,
+                            const uint8_t *active_dev, double *reward_dev, double *dmin_dev, int32_t *flags_dev,
+                            int32_t *nbr_dev, int32_t *nbr_cnt_dev, int32_t *status_dev, void *stream)
+{
+    return launch_crowd(cfg, door, reward_cfg, state, obs, robot_action_dev, active_dev, reward_dev, dmin_dev, flags_dev,
+                        nullptr, nbr_dev, nbr_cnt_dev, status_dev, 1, stream);
+}
+
+// ---- host-buffer single call: what policy.predict(state) does behind the rvo2 FFI ----
+namespace {
+struct PredictScratch {
+    double *d = nullptr;   // 8 (self) + 5*32 (others) + 2 (out)
+    int *i = nullptr;      // 32 nbr + 1 cnt + 1 status
+    double *h = nullptr;   // pinned mirror
+    int *hi = nullptr;
+    std::mutex mu;
+};
+PredictScratch g_ps;
+constexpr int PS_D = 8 + 5 * SNB_MAX_AGENTS_PER_ENV + 2;
+constexpr int PS_I = SNB_MAX_AGENTS_PER_ENV + 2;
+}
+
+extern "C" int snb_policy_predict_host(const SnbPolicyCfg *cfg, const double *self8, int32_t n_others, const double *others5,
+                                       int32_t n_seg, const double *segs, double *out_v2, int32_t *nbr_ids, int32_t *n_nbr)
+{
+    SNB_REQUIRE(cfg && self8 && out_v2, SNB_EINVAL, "snb_policy_predict_host: NULL argument");
+    SNB_REQUIRE(n_others >= 0 && n_others <= SNB_MAX_AGENTS_PER_ENV, SNB_EUNSUPPORTED, "snb_policy_predict_host: n_others=%d unsupported", n_others);
+    SNB_REQUIRE(n_others == 0 || others5, SNB_EINVAL, "snb_policy_predict_host: others is NULL");
+    std::lock_guard<std::mutex> lk(g_ps.mu);
+    if (!g_ps.d) {
+        SNB_CUDA_TRY(cudaMalloc(&g_ps.d, sizeof(double) * PS_D));
+        SNB_CUDA_TRY(cudaMalloc(&g_ps.i, sizeof(int) * PS_I));
+        SNB_CUDA_TRY(cudaMallocHost(&g_ps.h, sizeof(double) * PS_D));
+        SNB_CUDA_TRY(cudaMallocHost(&g_ps.hi, sizeof(int) * PS_I));
+    }
+    SnbObstacles *obs = nullptr;
+    if (n_seg > 0) { const int rc = snb_obstacles_create(&obs, segs, n_seg); if (rc) return rc; }
+    // SoA on the device: self arrays (1 each) then the extras arrays (n_others each)
+    double *h = g_ps.h;
+    const int N = n_others > 0 ? n_others : 1;
+    for (int k = 0; k < 8; ++k) h[k] = self8[k];
+    for (int j = 0; j < n_others; ++j)
+        for (int c = 0; c < 5; ++c) h[8 + c * N + j] = others5[5 * j + c];
+    cudaStream_t s = 0;
+    cudaError_t e = cudaMemcpyAsync(g_ps.d, h, sizeof(double) * (8 + 5 * N), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g_ps.i, 0, sizeof(int) * PS_I, s);
+    int rc = SNB_OK;
+    if (e == cudaSuccess) {
+        SnbCrowdState st;
+        memset(&st, 0, sizeof(st));
+        st.B = 1; st.H = 1; st.E = n_others; st.n_obs_extras = n_others;
+        double *d = g_ps.d;
+        st.px = d + 0; st.py = d + 1; st.vx = d + 2; st.vy = d + 3; st.radius = d + 4; st.gx = d + 5; st.gy = d + 6; st.vpref = d + 7;
+        st.ex_px = d + 8; st.ex_py = d + 8 + N; st.ex_vx = d + 8 + 2 * N; st.ex_vy = d + 8 + 3 * N; st.ex_radius = d + 8 + 4 * N;
+        double *d_out = d + 8 + 5 * SNB_MAX_AGENTS_PER_ENV;
+        rc = snb_policy_step(cfg, &st, obs, d_out, g_ps.i, g_ps.i + SNB_MAX_AGENTS_PER_ENV, g_ps.i + SNB_MAX_AGENTS_PER_ENV + 1, s);
+        if (rc == SNB_OK) {
+            e = cudaMemcpyAsync(h, d_out, sizeof(double) * 2, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(g_ps.hi, g_ps.i, sizeof(int) * PS_I, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        }
+    }
+    if (obs) snb_obstacles_destroy(obs);
+    if (rc) return rc;
+    if (e != cudaSuccess) { snb_set_error("snb_policy_predict_host: %s", cudaGetErrorString(e)); return SNB_ECUDA; }
+    if (g_ps.hi[SNB_MAX_AGENTS_PER_ENV + 1] != 0) { snb_set_error("snb_policy_predict_host: device capacity exceeded (ORCA lines / obstacle neighbours)"); return SNB_EOVERFLOW; }
+    out_v2[0] = h[0]; out_v2[1] = h[1];
+    if (n_nbr) {
+        *n_nbr = g_ps.hi[SNB_MAX_AGENTS_PER_ENV];
+        if (nbr_ids) for (int k = 0; k < *n_nbr; ++k) nbr_ids[k] = g_ps.hi[k] - 1; // agent id H+e with H=1 -> ob index e
+    }
+    return SNB_OK;
+}
