@@ -1,0 +1,336 @@
+// csrc/jmid_api.cu -- C-ABI entry points of the JMID / iMID denoiser (include/snb.h): model construction,
+// the batched DDIM sampling loop (DiffusionTraj.sample_sicnav_inference, models/diffusion.py:478-541), one-shot
+// eps, integration and the host-buffer plugin call.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "jmid_internal.h"
+
+namespace {
+
+constexpr int D = 512, DFF = 1024, NL = 3;
+
+struct LayerDev {
+    bf16 *wqkv, *wo, *w1, *w2;
+    float *bqkv, *bo, *b1, *b2, *n1w, *n1b, *n2w, *n2b;
+};
+
+struct Plans {
+    int n_env = 0, M = 0;
+    GemmPlan qkv[NL], out[NL], ff1[NL], ff2[NL], c3, c4;
+    AttnPlan attn;
+};
+
+} // namespace
+
+struct SnbJmid {
+    int A, S, T, joint, max_envs, chunk_envs, N /*tokens per env*/, num_sms;
+    std::vector<void *> allocs;
+    // weights
+    LayerDev L[NL];
+    bf16 *wc3, *wc4;
+    float *c1_w, *c1_b, *c3_b, *c4_b, *lin_w, *lin_b, *pe;
+    HyperW hyper[4];
+    float betas[101], alpha_bars[101];
+    // activations for one chunk
+    bf16 *h, *y, *qkv, *att, *ff, *t3, *t4;
+    float *pre, *xa, *xb, *gc, *bc, *gate, *hb;
+    std::map<int, Plans> plans;
+    // host-call staging
+    float *d_ctx = nullptr, *d_xT = nullptr, *d_p0 = nullptr, *d_vel = nullptr, *d_pos = nullptr;
+};
+
+namespace {
+
+template <class Tp>
+int dev_alloc(SnbJmid *h, Tp **p, size_t n)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(Tp));
+    if (e != cudaSuccess) { snb_set_error("snb_jmid: cudaMalloc(%zu B) failed: %s", n * sizeof(Tp), cudaGetErrorString(e)); return SNB_ENOMEM; }
+    h->allocs.push_back(q);
+    *p = static_cast<Tp *>(q);
+    return SNB_OK;
+}
+
+int dup_f32(SnbJmid *h, float **dst, const float *src, size_t n, cudaStream_t s)
+{
+    SNB_REQUIRE(src != nullptr, SNB_EINVAL, "snb_jmid_create: NULL weight pointer");
+    int rc = dev_alloc(h, dst, n);
+    if (rc) return rc;
+    SNB_CUDA_TRY(cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return SNB_OK;
+}
+
+int dup_bf16(SnbJmid *h, bf16 **dst, const float *src, size_t n, cudaStream_t s)
+{
+    SNB_REQUIRE(src != nullptr, SNB_EINVAL, "snb_jmid_create: NULL weight pointer");
+    int rc = dev_alloc(h, dst, n);
+    if (rc) return rc;
+    return snb_k_f32_to_bf16(src, *dst, n, s);
+}
+
+int get_plans(SnbJmid *h, int n_env, Plans **out)
+{
+    auto it = h->plans.find(n_env);
+    if (it != h->plans.end()) { *out = &it->second; return SNB_OK; }
+    Plans p;
+    p.n_env = n_env;
+    p.M = n_env * h->N;
+    int rc = 0;
+    for (int l = 0; l < NL && !rc; ++l) {
+        rc = snb_gemm_plan(&p.qkv[l], h->h, h->L[l].wqkv, p.M, 3 * D, D);
+        if (!rc) rc = snb_gemm_plan(&p.out[l], h->att, h->L[l].wo, p.M, D, D);
+        if (!rc) rc = snb_gemm_plan(&p.ff1[l], h->y, h->L[l].w1, p.M, DFF, D);
+        if (!rc) rc = snb_gemm_plan(&p.ff2[l], h->ff, h->L[l].w2, p.M, D, DFF);
+    }
+    if (!rc) rc = snb_gemm_plan(&p.c3, h->h, h->wc3, p.M, 256, D);
+    if (!rc) rc = snb_gemm_plan(&p.c4, h->t3, h->wc4, p.M, 128, 256);
+    if (!rc && h->joint) rc = snb_attn_plan(&p.attn, h->qkv, n_env, h->N);
+    if (rc) return rc;
+    h->plans[n_env] = p;
+    *out = &h->plans[n_env];
+    return SNB_OK;
+}
+
+// one noise-network forward for the chunk currently staged in h->gc / h->bc / x_in (diffusion.py:173-209)
+int net_forward(SnbJmid *h, Plans *P, const float *x_in, float *x_next, float *eps_out, int t, int t_next, cudaStream_t s)
+{
+    const int M = P->M, n_ba = P->n_env * h->A;
+    int rc = snb_k_hyper_iter(h->hyper, h->gc, h->bc, h->gate, h->hb, n_ba, h->betas[t], s);
+    if (rc) return rc;
+    rc = snb_k_embed(x_in, h->c1_w, h->c1_b, h->gate, h->hb, h->pe, h->h, M, h->N, h->T, h->A, s);
+    if (rc) return rc;
+    GemmEpi e;
+    for (int l = 0; l < NL; ++l) {
+        memset(&e, 0, sizeof(e));
+        e.bias = h->L[l].bqkv; e.out = h->qkv; e.ldo = 3 * D;
+        if ((rc = snb_gemm_launch(&P->qkv[l], EPI_BIAS_BF16, &e, h->num_sms, s))) return rc;
+        if (h->joint) rc = snb_attn_launch(&P->attn, h->att, s);
+        else rc = snb_attn_small_launch(h->qkv, h->att, M / h->T, h->T, s);
+        if (rc) return rc;
+        memset(&e, 0, sizeof(e));
+        e.bias = h->L[l].bo; e.out = h->pre; e.ldo = D; e.resid = h->h; e.ldr = D;
+        if ((rc = snb_gemm_launch(&P->out[l], EPI_BIAS_RESID_F32, &e, h->num_sms, s))) return rc;
+        if ((rc = snb_k_layernorm(h->pre, h->L[l].n1w, h->L[l].n1b, h->y, M, s))) return rc;
+        memset(&e, 0, sizeof(e));
+        e.bias = h->L[l].b1; e.out = h->ff; e.ldo = DFF;
+        if ((rc = snb_gemm_launch(&P->ff1[l], EPI_BIAS_RELU_BF16, &e, h->num_sms, s))) return rc;
+        memset(&e, 0, sizeof(e));
+        e.bias = h->L[l].b2; e.out = h->pre; e.ldo = D; e.resid = h->y; e.ldr = D;
+        if ((rc = snb_gemm_launch(&P->ff2[l], EPI_BIAS_RESID_F32, &e, h->num_sms, s))) return rc;
+        if ((rc = snb_k_layernorm(h->pre, h->L[l].n2w, h->L[l].n2b, h->h, M, s))) return rc;
+    }
+    memset(&e, 0, sizeof(e));
+    e.bias = h->c3_b; e.out = h->t3; e.ldo = 256; e.gate = h->gate + 512; e.hbias = h->hb + 512; e.tab_ld = HYPER_LD;
+    e.tok_per_env = h->N; e.T = h->T; e.A = h->A;
+    if ((rc = snb_gemm_launch(&P->c3, EPI_CSL_BF16, &e, h->num_sms, s))) return rc;
+    e.bias = h->c4_b; e.out = h->t4; e.ldo = 128; e.gate = h->gate + 768; e.hbias = h->hb + 768;
+    if ((rc = snb_gemm_launch(&P->c4, EPI_CSL_BF16, &e, h->num_sms, s))) return rc;
+    // DDIM coefficients in fp32 like torch: (1 - ab).sqrt(), ab.sqrt(), ab_next.sqrt(), (1 - ab_next).sqrt()
+    const float ab = h->alpha_bars[t], abn = h->alpha_bars[t_next];
+    return snb_k_tail_ddim(h->t4, h->lin_w, h->lin_b, h->gate + 896, h->hb + 896, HYPER_LD, x_in, x_next, eps_out, M, h->N, h->T,
+                           h->A, sqrtf(1.0f - ab), sqrtf(ab), sqrtf(abn), sqrtf(1.0f - abn), s);
+}
+
+} // namespace
+
+extern "C" double snb_jmid_flops_per_iter(int32_t A, int32_t S, int32_t T, int32_t joint)
+{
+    const double N = (double)A * S * T, R = (double)A * S;
+    const double dense = 12913152.0 * N;
+    return dense + (joint ? 6144.0 * N * N : 6144.0 * R * T * T);
+}
+
+extern "C" int snb_jmid_create(SnbJmid **out, const SnbJmidWeights *w, int32_t max_envs, int32_t A, int32_t S, int32_t T,
+                               int32_t joint, void *stream)
+{
+    SNB_REQUIRE(out && w, SNB_EINVAL, "snb_jmid_create: NULL argument");
+    SNB_REQUIRE(max_envs >= 1 && A >= 1 && S >= 1 && T >= 1 && T <= 24, SNB_EINVAL, "snb_jmid_create: bad sizes (T <= 24 = pos_emb max_len)");
+    int dev = 0, cc_major = 0;
+    SNB_CUDA_TRY(cudaGetDevice(&dev));
+    SNB_CUDA_TRY(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    SNB_REQUIRE(cc_major == 10, SNB_ECUDA, "snb_jmid_create: the denoiser kernels are sm_100a only (device is sm_%d)", cc_major * 10);
+    cudaStream_t s = (cudaStream_t)stream;
+    SnbJmid *h = new SnbJmid();
+    h->A = A; h->S = S; h->T = T; h->joint = joint ? 1 : 0; h->max_envs = max_envs; h->N = A * S * T;
+    SNB_CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev));
+    const char *ce = getenv("SNB_JMID_CHUNK");
+    int chunk = ce ? atoi(ce) : 16;
+    if (chunk < 1) chunk = 1;
+    h->chunk_envs = chunk < max_envs ? chunk : max_envs;
+    int rc = 0;
+#define TRY(x) do { if (!rc) rc = (x); } while (0)
+    const SnbCslWeights *csl[4] = {&w->concat1, &w->concat3, &w->concat4, &w->linear};
+    const int douts[4] = {512, 256, 128, 2};
+    for (int i = 0; i < 4; ++i) {
+        float *gw = nullptr, *gb = nullptr, *bw = nullptr;
+        TRY(dup_f32(h, &gw, (const float *)csl[i]->hyper_gate_w, (size_t)douts[i] * 259, s));
+        TRY(dup_f32(h, &gb, (const float *)csl[i]->hyper_gate_b, (size_t)douts[i], s));
+        TRY(dup_f32(h, &bw, (const float *)csl[i]->hyper_bias_w, (size_t)douts[i] * 259, s));
+        h->hyper[i].gate_w = gw; h->hyper[i].gate_b = gb; h->hyper[i].bias_w = bw; h->hyper[i].dout = douts[i];
+    }
+    TRY(dup_f32(h, &h->c1_w, (const float *)w->concat1.layer_w, 512 * 2, s));
+    TRY(dup_f32(h, &h->c1_b, (const float *)w->concat1.layer_b, 512, s));
+    TRY(dup_bf16(h, &h->wc3, (const float *)w->concat3.layer_w, 256 * 512, s));
+    TRY(dup_f32(h, &h->c3_b, (const float *)w->concat3.layer_b, 256, s));
+    TRY(dup_bf16(h, &h->wc4, (const float *)w->concat4.layer_w, 128 * 256, s));
+    TRY(dup_f32(h, &h->c4_b, (const float *)w->concat4.layer_b, 128, s));
+    TRY(dup_f32(h, &h->lin_w, (const float *)w->linear.layer_w, 2 * 128, s));
+    TRY(dup_f32(h, &h->lin_b, (const float *)w->linear.layer_b, 2, s));
+    TRY(dup_f32(h, &h->pe, (const float *)w->pos_emb, (size_t)T * 512, s));
+    for (int l = 0; l < NL; ++l) {
+        const SnbEncLayerWeights &lw = w->layers[l];
+        TRY(dup_bf16(h, &h->L[l].wqkv, (const float *)lw.in_proj_w, (size_t)3 * D * D, s));
+        TRY(dup_f32(h, &h->L[l].bqkv, (const float *)lw.in_proj_b, 3 * D, s));
+        TRY(dup_bf16(h, &h->L[l].wo, (const float *)lw.out_proj_w, (size_t)D * D, s));
+        TRY(dup_f32(h, &h->L[l].bo, (const float *)lw.out_proj_b, D, s));
+        TRY(dup_bf16(h, &h->L[l].w1, (const float *)lw.lin1_w, (size_t)DFF * D, s));
+        TRY(dup_f32(h, &h->L[l].b1, (const float *)lw.lin1_b, DFF, s));
+        TRY(dup_bf16(h, &h->L[l].w2, (const float *)lw.lin2_w, (size_t)D * DFF, s));
+        TRY(dup_f32(h, &h->L[l].b2, (const float *)lw.lin2_b, D, s));
+        TRY(dup_f32(h, &h->L[l].n1w, (const float *)lw.norm1_w, D, s));
+        TRY(dup_f32(h, &h->L[l].n1b, (const float *)lw.norm1_b, D, s));
+        TRY(dup_f32(h, &h->L[l].n2w, (const float *)lw.norm2_w, D, s));
+        TRY(dup_f32(h, &h->L[l].n2b, (const float *)lw.norm2_b, D, s));
+    }
+    const size_t Mc = (size_t)h->chunk_envs * h->N;
+    const size_t Mp = ((Mc + 127) / 128) * 128; // padded so that tensor-map boxes never leave the allocation
+    TRY(dev_alloc(h, &h->h, Mp * D));
+    TRY(dev_alloc(h, &h->y, Mp * D));
+    TRY(dev_alloc(h, &h->qkv, Mp * 3 * D));
+    TRY(dev_alloc(h, &h->att, Mp * D));
+    TRY(dev_alloc(h, &h->ff, Mp * DFF));
+    TRY(dev_alloc(h, &h->t3, Mp * 256));
+    TRY(dev_alloc(h, &h->t4, Mp * 128));
+    TRY(dev_alloc(h, &h->pre, Mp * D));
+    TRY(dev_alloc(h, &h->xa, Mp * 2));
+    TRY(dev_alloc(h, &h->xb, Mp * 2));
+    const size_t nba = (size_t)h->chunk_envs * A;
+    TRY(dev_alloc(h, &h->gc, nba * HYPER_LD));
+    TRY(dev_alloc(h, &h->bc, nba * HYPER_LD));
+    TRY(dev_alloc(h, &h->gate, nba * HYPER_LD));
+    TRY(dev_alloc(h, &h->hb, nba * HYPER_LD));
+#undef TRY
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(h->betas, w->betas, sizeof(float) * 101, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h->alpha_bars, w->alpha_bars, sizeof(float) * 101, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { snb_set_error("snb_jmid_create: %s", cudaGetErrorString(e)); rc = SNB_ECUDA; }
+    }
+    if (rc) { snb_jmid_destroy(h); return rc; }
+    *out = h;
+    return SNB_OK;
+}
+
+extern "C" int snb_jmid_destroy(SnbJmid *h)
+{
+    if (!h) return SNB_OK;
+    for (void *p : h->allocs) cudaFree(p);
+    cudaFree(h->d_ctx); cudaFree(h->d_xT); cudaFree(h->d_p0); cudaFree(h->d_vel); cudaFree(h->d_pos);
+    delete h;
+    return SNB_OK;
+}
+
+extern "C" int snb_jmid_denoise(SnbJmid *h, const float *ctx, const float *x_T, float *out_vel, int32_t B, int32_t n_steps, void *stream)
+{
+    SNB_REQUIRE(h && ctx && x_T && out_vel, SNB_EINVAL, "snb_jmid_denoise: NULL argument");
+    SNB_REQUIRE(B >= 0 && n_steps >= 1 && n_steps <= 100, SNB_EINVAL, "snb_jmid_denoise: bad B / n_steps");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int stride = 100 / n_steps; // int(100 / step), diffusion.py:507
+    for (int e0 = 0; e0 < B; e0 += h->chunk_envs) {
+        const int ne = (B - e0) < h->chunk_envs ? (B - e0) : h->chunk_envs;
+        Plans *P = nullptr;
+        int rc = get_plans(h, ne, &P);
+        if (rc) return rc;
+        const size_t M = (size_t)P->M;
+        if ((rc = snb_k_hyper_ctx(h->hyper, ctx + (size_t)e0 * h->A * 256, h->gc, h->bc, ne * h->A, s))) return rc;
+        SNB_CUDA_TRY(cudaMemcpyAsync(h->xa, x_T + (size_t)e0 * h->N * 2, M * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        float *cur = h->xa, *nxt = h->xb;
+        for (int t = 100; t > 0; t -= stride) {
+            if ((rc = net_forward(h, P, cur, nxt, nullptr, t, t - stride, s))) return rc;
+            float *tmp = cur; cur = nxt; nxt = tmp;
+        }
+        SNB_CUDA_TRY(cudaMemcpyAsync(out_vel + (size_t)e0 * h->N * 2, cur, M * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    return SNB_OK;
+}
+
+extern "C" int snb_jmid_eps(SnbJmid *h, const float *ctx, const float *x_t, float *eps, int32_t B, int32_t t, void *stream)
+{
+    SNB_REQUIRE(h && ctx && x_t && eps, SNB_EINVAL, "snb_jmid_eps: NULL argument");
+    SNB_REQUIRE(t >= 1 && t <= 100, SNB_EINVAL, "snb_jmid_eps: t out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int e0 = 0; e0 < B; e0 += h->chunk_envs) {
+        const int ne = (B - e0) < h->chunk_envs ? (B - e0) : h->chunk_envs;
+        Plans *P = nullptr;
+        int rc = get_plans(h, ne, &P);
+        if (rc) return rc;
+        if ((rc = snb_k_hyper_ctx(h->hyper, ctx + (size_t)e0 * h->A * 256, h->gc, h->bc, ne * h->A, s))) return rc;
+        if ((rc = net_forward(h, P, x_t + (size_t)e0 * h->N * 2, nullptr, eps + (size_t)e0 * h->N * 2, t, t - 1, s))) return rc;
+    }
+    return SNB_OK;
+}
+
+extern "C" int snb_jmid_integrate(const float *vel, const float *p0, float *pos, int32_t B, int32_t S, int32_t A, int32_t T,
+                                  float dt, void *stream)
+{
+    SNB_REQUIRE(vel && p0 && pos, SNB_EINVAL, "snb_jmid_integrate: NULL argument");
+    if (B == 0) return SNB_OK;
+    return snb_k_integrate(vel, p0, pos, B, S, A, T, dt, (cudaStream_t)stream);
+}
+
+extern "C" int snb_jmid_predict_host(SnbJmid *h, const float *ctx_host, const float *x_T_host, const float *p0_host,
+                                     float *pos_host, int32_t B, int32_t n_steps, float dt)
+{
+    SNB_REQUIRE(h && ctx_host && x_T_host && p0_host && pos_host, SNB_EINVAL, "snb_jmid_predict_host: NULL argument");
+    SNB_REQUIRE(B >= 1 && B <= h->max_envs, SNB_EINVAL, "snb_jmid_predict_host: B=%d beyond max_envs=%d", B, h->max_envs);
+    if (!h->d_ctx) {
+        const size_t me = (size_t)h->max_envs;
+        SNB_CUDA_TRY(cudaMalloc(&h->d_ctx, me * h->A * 256 * sizeof(float)));
+        SNB_CUDA_TRY(cudaMalloc(&h->d_xT, me * h->N * 2 * sizeof(float)));
+        SNB_CUDA_TRY(cudaMalloc(&h->d_p0, me * h->A * 2 * sizeof(float)));
+        SNB_CUDA_TRY(cudaMalloc(&h->d_vel, me * h->N * 2 * sizeof(float)));
+        SNB_CUDA_TRY(cudaMalloc(&h->d_pos, me * h->N * 2 * sizeof(float)));
+    }
+    cudaStream_t s = 0;
+    SNB_CUDA_TRY(cudaMemcpyAsync(h->d_ctx, ctx_host, (size_t)B * h->A * 256 * sizeof(float), cudaMemcpyHostToDevice, s));
+    SNB_CUDA_TRY(cudaMemcpyAsync(h->d_xT, x_T_host, (size_t)B * h->N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    SNB_CUDA_TRY(cudaMemcpyAsync(h->d_p0, p0_host, (size_t)B * h->A * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = snb_jmid_denoise(h, h->d_ctx, h->d_xT, h->d_vel, B, n_steps, s);
+    if (rc) return rc;
+    rc = snb_jmid_integrate(h->d_vel, h->d_p0, h->d_pos, B, h->S, h->A, h->T, dt, s);
+    if (rc) return rc;
+    SNB_CUDA_TRY(cudaMemcpyAsync(pos_host, h->d_pos, (size_t)B * h->N * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    SNB_CUDA_TRY(cudaStreamSynchronize(s));
+    return SNB_OK;
+}
+
+extern "C" int snb_jmid_gemm_bf16(const void *A, const void *W, const float *bias, const void *resid, void *out, int32_t M,
+                                  int32_t N, int32_t K, int32_t epi, void *stream)
+{
+    SNB_REQUIRE(A && W && bias && out, SNB_EINVAL, "snb_jmid_gemm_bf16: NULL argument");
+    SNB_REQUIRE(epi >= 0 && epi <= 2 && (epi != 2 || resid), SNB_EINVAL, "snb_jmid_gemm_bf16: bad epilogue");
+    int dev = 0, sms = 0;
+    SNB_CUDA_TRY(cudaGetDevice(&dev));
+    SNB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GemmPlan p;
+    int rc = snb_gemm_plan(&p, (const bf16 *)A, (const bf16 *)W, M, N, K);
+    if (rc) return rc;
+    GemmEpi e;
+    memset(&e, 0, sizeof(e));
+    e.bias = bias; e.out = out; e.ldo = N; e.resid = (const bf16 *)resid; e.ldr = N;
+    return snb_gemm_launch(&p, epi, &e, sms, (cudaStream_t)stream);
+}
+
+extern "C" int snb_jmid_attention(const void *qkv, void *out, int32_t n_env, int32_t n_tok, void *stream)
+{
+    SNB_REQUIRE(qkv && out, SNB_EINVAL, "snb_jmid_attention: NULL argument");
+    AttnPlan p;
+    int rc = snb_attn_plan(&p, (const bf16 *)qkv, n_env, n_tok);
+    if (rc) return rc;
+    return snb_attn_launch(&p, (bf16 *)out, (cudaStream_t)stream);
+}

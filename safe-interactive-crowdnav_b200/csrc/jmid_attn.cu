@@ -1,0 +1,322 @@
+// csrc/jmid_attn.cu -- fused multi-head self-attention of the JMID noise network on tcgen05.
+//
+// The reference flattens the T*A*S tokens of one environment into ONE unmasked sequence and runs
+// nn.MultiheadAttention(d=512, heads=4) over it (models/diffusion.py:196-204, quirk q1).  This kernel computes, per
+// (environment, head, 128-query tile):  O = softmax(Q K^T / sqrt(128)) V  flash-style, never materialising the
+// N x N score matrix in HBM:
+//   warp 0      TMA producer: Q tile once, then K / V blocks of 128 keys through 2-stage smem rings
+//   warp 1      MMA issuer:   S = Q K^T (SS, M=128 N<=128 K=128) into a double-buffered TMEM S tile,
+//                             O += P V (TS: P read from TMEM as bf16, V MN-major from smem) into a TMEM O tile
+//   warp 2      TMEM allocator
+//   warps 4..7  softmax:      one thread per query row: tcgen05.ld the S row, running max with lazy rescale of O,
+//                             exp2, bf16 P written back over S with tcgen05.st, final O / l -> global
+// S(j+1) is issued before waiting for P(j), so the QK^T of the next block overlaps the softmax of the current one.
+#include <cfloat>
+#include <mutex>
+
+#include "jmid_internal.h"
+#include "tc_utils.cuh"
+
+namespace {
+
+constexpr int HD = 128;       // head dim
+constexpr int NHEAD = 4;
+constexpr int BQ = 128;       // queries per CTA
+constexpr int BKV = 128;      // keys per block
+constexpr int KV_STAGES = 2;
+constexpr int TILE_BYTES = BQ * HD * 2; // 32 KB: two 64-column boxes of 16 KB
+constexpr int ATTN_THREADS = 256;
+constexpr int ATTN_SMEM = TILE_BYTES * (1 + 2 * KV_STAGES) + 1024 + 256;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O = 256;
+constexpr float RESCALE_THRESHOLD = 8.0f; // log2 units: P <= 2^8 before the running max is refreshed
+
+struct AttnArgs {
+    bf16 *out;        // [n_env * n_tok, 512]
+    int n_tok;
+    float scale_log2; // log2(e) / sqrt(HD)
+};
+
+__global__ void __launch_bounds__(ATTN_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sQ = smem;
+    uint8_t *sK = smem + TILE_BYTES;
+    uint8_t *sV = smem + TILE_BYTES * (1 + KV_STAGES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TILE_BYTES * (1 + 2 * KV_STAGES));
+    uint64_t *q_full = bars;
+    uint64_t *k_full = bars + 1, *k_empty = bars + 3, *v_full = bars + 5, *v_empty = bars + 7;
+    uint64_t *s_full = bars + 9, *p_ready = bars + 11, *pv_done = bars + 13;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 15);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * BQ, head = blockIdx.y, env = blockIdx.z;
+    const int n_tok = args.n_tok;
+    const int n_kv = (n_tok + BKV - 1) / BKV;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmQKV);
+        tc::mbar_init(q_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1);
+            tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], 1);
+            tc::mbar_init(&s_full[s], 1); tc::mbar_init(&p_ready[s], 128); tc::mbar_init(&pv_done[s], 1);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const int cq = head * HD, ck = 512 + head * HD, cv = 1024 + head * HD;
+            tc::mbar_arrive_expect_tx(q_full, TILE_BYTES);
+            tc::tma_load_3d(sQ, &tmQKV, q_full, cq, q0, env);
+            tc::tma_load_3d(sQ + TILE_BYTES / 2, &tmQKV, q_full, cq + 64, q0, env);
+            for (int j = 0; j < n_kv; ++j) {
+                const int st = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
+                tc::mbar_wait(&k_empty[st], ph ^ 1);
+                tc::mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
+                tc::tma_load_3d(sK + st * TILE_BYTES, &tmQKV, &k_full[st], ck, j * BKV, env);
+                tc::tma_load_3d(sK + st * TILE_BYTES + TILE_BYTES / 2, &tmQKV, &k_full[st], ck + 64, j * BKV, env);
+                tc::mbar_wait(&v_empty[st], ph ^ 1);
+                tc::mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
+                tc::tma_load_3d(sV + st * TILE_BYTES, &tmQKV, &v_full[st], cv, j * BKV, env);
+                tc::tma_load_3d(sV + st * TILE_BYTES + TILE_BYTES / 2, &tmQKV, &v_full[st], cv + 64, j * BKV, env);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t q_addr = tc::smem_u32(sQ);
+            auto kv_cols = [&](int j) { // keys of block j rounded up to the UMMA N granularity (16)
+                const int rem = n_tok - j * BKV;
+                return rem >= BKV ? BKV : ((rem + 15) & ~15);
+            };
+            auto issue_S = [&](int j) {
+                const int st = j & 1;
+                tc::mbar_wait(&k_full[st], (j >> 1) & 1);
+                tc::tc_fence_after();
+                const uint32_t k_addr = tc::smem_u32(sK + st * TILE_BYTES);
+                const uint32_t idesc = tc::make_idesc_bf16(BQ, (uint32_t)kv_cols(j), 0, 0);
+                const uint32_t d = tmem_base + (st ? TM_S1 : TM_S0);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) {
+                    const uint32_t off = (k >> 2) * (TILE_BYTES / 2) + (k & 3) * 32;
+                    tc::umma_ss(d, tc::make_smem_desc_sw128(q_addr + off, 16, 1024), tc::make_smem_desc_sw128(k_addr + off, 16, 1024),
+                                idesc, k != 0 ? 1u : 0u);
+                }
+                tc::umma_commit(&k_empty[st]);
+                tc::umma_commit(&s_full[st]);
+            };
+            tc::mbar_wait(q_full, 0);
+            tc::tc_fence_after();
+            issue_S(0);
+            constexpr uint32_t idesc_pv = tc::make_idesc_bf16(BQ, HD, 0, 1); // B = V is MN-major (head dim contiguous)
+            for (int j = 0; j < n_kv; ++j) {
+                const int st = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
+                if (j + 1 < n_kv) issue_S(j + 1);
+                tc::mbar_wait(&p_ready[st], ph);
+                tc::mbar_wait(&v_full[st], ph);
+                tc::tc_fence_after();
+                const uint32_t v_addr = tc::smem_u32(sV + st * TILE_BYTES);
+                const uint32_t p_tmem = tmem_base + (st ? TM_S1 : TM_S0);
+                const int ksteps = kv_cols(j) / 16;
+                for (int k = 0; k < ksteps; ++k) {
+                    // 16 keys = 2 groups of 8 rows (SBO 1024 B); the two 64-wide head-dim boxes are LBO = 16 KB apart
+                    const uint64_t dv = tc::make_smem_desc_sw128(v_addr + k * 2048, TILE_BYTES / 2, 1024);
+                    tc::umma_ts(tmem_base + TM_O, p_tmem + k * 8, dv, idesc_pv, (j | k) != 0 ? 1u : 0u);
+                }
+                tc::umma_commit(&v_empty[st]);
+                tc::umma_commit(&pv_done[st]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== softmax / correction / epilogue =====================
+        const int quarter = warp & 3;
+        const int row_in_tile = quarter * 32 + lane;
+        const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
+        const float c = args.scale_log2;
+        float m_used = -INFINITY; // running max the exponents are taken against (raw score units)
+        float l = 0.0f;
+        for (int j = 0; j < n_kv; ++j) {
+            const int st = j & 1;
+            const uint32_t ph = (j >> 1) & 1;
+            tc::mbar_wait(&s_full[st], ph);
+            tc::tc_fence_after();
+            const uint32_t s_addr = tmem_base + lane_addr + (st ? TM_S1 : TM_S0);
+            float s[BKV];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t r[32];
+                tc::tmem_ld_32x32(s_addr + ch * 32, r);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) s[ch * 32 + i] = __uint_as_float(r[i]);
+            }
+            const int valid = n_tok - j * BKV; // keys of this block that exist
+            float bmax = -INFINITY;
+            if (valid >= BKV) {
+#pragma unroll
+                for (int i = 0; i < BKV; ++i) bmax = fmaxf(bmax, s[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < BKV; ++i) { if (i >= valid) s[i] = -INFINITY; bmax = fmaxf(bmax, s[i]); }
+            }
+            if (j == 0) {
+                m_used = bmax;
+            } else if ((bmax - m_used) * c > RESCALE_THRESHOLD) {
+                // refresh the running max: O and l are rescaled once the previous PV has landed
+                const int pst = (j - 1) & 1;
+                tc::mbar_wait(&pv_done[pst], ((j - 1) >> 1) & 1);
+                tc::tc_fence_after();
+                const float f = exp2f((m_used - bmax) * c);
+                const uint32_t o_addr = tmem_base + lane_addr + TM_O;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t r[32];
+                    tc::tmem_ld_32x32(o_addr + ch * 32, r);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+                    tc::tmem_st_32x32(o_addr + ch * 32, r);
+                }
+                l *= f;
+                m_used = bmax;
+            }
+            const float mc = m_used * c;
+            float sum = 0.0f;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                uint32_t pk[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float p0 = exp2f(fmaf(s[ch * 64 + 2 * i], c, -mc));
+                    const float p1 = exp2f(fmaf(s[ch * 64 + 2 * i + 1], c, -mc));
+                    sum += p0 + p1;
+                    pk[i] = tc::pack_bf16(p0, p1);
+                }
+                tc::tmem_st_32x32(s_addr + ch * 32, pk); // P (bf16 pairs) overwrites the first 64 columns of S
+            }
+            l += sum;
+            tc::tmem_st_wait();
+            tc::tc_fence_before();
+            tc::mbar_arrive(&p_ready[st]);
+        }
+        // final: O / l -> global
+        const int lst = (n_kv - 1) & 1;
+        tc::mbar_wait(&pv_done[lst], ((n_kv - 1) >> 1) & 1);
+        tc::tc_fence_after();
+        const float inv_l = 1.0f / l;
+        const int row = q0 + row_in_tile;
+        const uint32_t o_addr = tmem_base + lane_addr + TM_O;
+        bf16 *dst = args.out + ((size_t)env * n_tok + row) * (NHEAD * HD) + head * HD;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            uint32_t r[32];
+            tc::tmem_ld_32x32(o_addr + ch * 32, r);
+            tc::tmem_ld_wait();
+            if (row < n_tok) {
+                uint4 *o4 = reinterpret_cast<uint4 *>(dst + ch * 32);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4 o;
+                    o.x = tc::pack_bf16(__uint_as_float(r[8 * q + 0]) * inv_l, __uint_as_float(r[8 * q + 1]) * inv_l);
+                    o.y = tc::pack_bf16(__uint_as_float(r[8 * q + 2]) * inv_l, __uint_as_float(r[8 * q + 3]) * inv_l);
+                    o.z = tc::pack_bf16(__uint_as_float(r[8 * q + 4]) * inv_l, __uint_as_float(r[8 * q + 5]) * inv_l);
+                    o.w = tc::pack_bf16(__uint_as_float(r[8 * q + 6]) * inv_l, __uint_as_float(r[8 * q + 7]) * inv_l);
+                    o4[q] = o;
+                }
+            }
+        }
+        tc::tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// iMID: R independent sequences of T <= 32 tokens (TransformerConcatLinear, diffusion.py:147).  One warp per
+// (sequence, head); 8x8 scores are far below tensor-core tile sizes, so this runs on the CUDA cores.
+__global__ void attn_small_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, int n_seq, int T, float scale)
+{
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gw >= n_seq * NHEAD) return;
+    const int seq = gw / NHEAD, head = gw % NHEAD;
+    const bf16 *base = qkv + (size_t)seq * T * 1536 + head * HD;
+    // lane owns head-dim elements [4*lane, 4*lane+4)
+    for (int i = 0; i < T; ++i) {
+        float q[4];
+        const uint2 qv = *reinterpret_cast<const uint2 *>(base + (size_t)i * 1536 + 4 * lane);
+        const __nv_bfloat162 qa = *reinterpret_cast<const __nv_bfloat162 *>(&qv.x), qb = *reinterpret_cast<const __nv_bfloat162 *>(&qv.y);
+        q[0] = __bfloat162float(qa.x); q[1] = __bfloat162float(qa.y); q[2] = __bfloat162float(qb.x); q[3] = __bfloat162float(qb.y);
+        float sc[32];
+        float mx = -INFINITY;
+        for (int j = 0; j < T; ++j) {
+            const uint2 kv = *reinterpret_cast<const uint2 *>(base + 512 + (size_t)j * 1536 + 4 * lane);
+            const __nv_bfloat162 ka = *reinterpret_cast<const __nv_bfloat162 *>(&kv.x), kb = *reinterpret_cast<const __nv_bfloat162 *>(&kv.y);
+            float d = q[0] * __bfloat162float(ka.x) + q[1] * __bfloat162float(ka.y) + q[2] * __bfloat162float(kb.x) + q[3] * __bfloat162float(kb.y);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            sc[j] = d * scale;
+            mx = fmaxf(mx, sc[j]);
+        }
+        float den = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < T; ++j) {
+            const float p = __expf(sc[j] - mx);
+            den += p;
+            const uint2 vv = *reinterpret_cast<const uint2 *>(base + 1024 + (size_t)j * 1536 + 4 * lane);
+            const __nv_bfloat162 va = *reinterpret_cast<const __nv_bfloat162 *>(&vv.x), vb = *reinterpret_cast<const __nv_bfloat162 *>(&vv.y);
+            acc[0] += p * __bfloat162float(va.x); acc[1] += p * __bfloat162float(va.y);
+            acc[2] += p * __bfloat162float(vb.x); acc[3] += p * __bfloat162float(vb.y);
+        }
+        const float inv = 1.0f / den;
+        uint2 o;
+        o.x = tc::pack_bf16(acc[0] * inv, acc[1] * inv);
+        o.y = tc::pack_bf16(acc[2] * inv, acc[3] * inv);
+        *reinterpret_cast<uint2 *>(out + ((size_t)seq * T + i) * 512 + head * HD + 4 * lane) = o;
+    }
+}
+
+} // namespace
+
+int snb_attn_plan(AttnPlan *plan, const bf16 *qkv, int n_env, int n_tok)
+{
+    SNB_REQUIRE(n_env > 0 && n_tok > 0, SNB_EINVAL, "attention: bad sizes");
+    plan->n_env = n_env; plan->n_tok = n_tok;
+    return snb_make_tmap_3d(&plan->tmQKV, qkv, (uint64_t)n_env, (uint64_t)n_tok, 1536, BKV);
+}
+
+int snb_attn_launch(const AttnPlan *plan, bf16 *out, cudaStream_t stream)
+{
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM); });
+    SNB_CUDA_TRY(attr_err);
+    AttnArgs a;
+    a.out = out; a.n_tok = plan->n_tok;
+    a.scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
+    dim3 grid((plan->n_tok + BQ - 1) / BQ, NHEAD, plan->n_env);
+    attn_fwd_kernel<<<grid, ATTN_THREADS, ATTN_SMEM, stream>>>(plan->tmQKV, a);
+    snb_count_launch();
+    SNB_CUDA_TRY(cudaGetLastError());
+    return SNB_OK;
+}
+
+int snb_attn_small_launch(const bf16 *qkv, bf16 *out, int n_seq, int T, cudaStream_t stream)
+{
+    SNB_REQUIRE(T >= 1 && T <= 32, SNB_EUNSUPPORTED, "attention(iMID): T=%d unsupported", T);
+    const int warps = n_seq * NHEAD;
+    const int threads = 256;
+    attn_small_kernel<<<(warps * 32 + threads - 1) / threads, threads, 0, stream>>>(qkv, out, n_seq, T, 1.0f / sqrtf((float)HD));
+    snb_count_launch();
+    SNB_CUDA_TRY(cudaGetLastError());
+    return SNB_OK;
+}

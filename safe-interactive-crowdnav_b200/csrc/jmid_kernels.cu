@@ -1,0 +1,252 @@
+// csrc/jmid_kernels.cu -- the HBM-bound pieces of the JMID noise network around the tensor-core kernels:
+// weight conversion, hyper-network (ConcatSquash gate / bias) tables, concat1 + positional encoding, LayerNorm,
+// the 128 -> 2 output layer fused with the DDIM update, and the single-integrator cumsum.
+// Reference: sicnav_diffusion/JMID/MID/models/common.py:37-72, models/diffusion.py:173-209, 507-531.
+#include "jmid_internal.h"
+#include "tc_utils.cuh"
+
+namespace {
+
+__global__ void f32_to_bf16_kernel(const float *__restrict__ src, bf16 *__restrict__ dst, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+struct Hyper4 { HyperW l[4]; };
+
+// one block per (ba); threads stride over the 898 output columns; ctx row staged in shared memory
+__global__ void hyper_ctx_kernel(const Hyper4 hw, const float *__restrict__ ctx, float *__restrict__ gc, float *__restrict__ bc)
+{
+    __shared__ float s_ctx[256];
+    const int ba = blockIdx.x;
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) s_ctx[k] = ctx[(size_t)ba * 256 + k];
+    __syncthreads();
+    for (int col = threadIdx.x; col < HYPER_TOTAL; col += blockDim.x) {
+        int li = 0, n = col;
+        while (n >= hw.l[li].dout) { n -= hw.l[li].dout; ++li; }
+        const float *wg = hw.l[li].gate_w + (size_t)n * 259 + 3;
+        const float *wb = hw.l[li].bias_w + (size_t)n * 259 + 3;
+        float g = hw.l[li].gate_b[n], b = 0.0f;
+#pragma unroll 4
+        for (int k = 0; k < 256; ++k) { g = fmaf(wg[k], s_ctx[k], g); b = fmaf(wb[k], s_ctx[k], b); }
+        gc[(size_t)ba * HYPER_LD + col] = g;
+        bc[(size_t)ba * HYPER_LD + col] = b;
+    }
+}
+
+__global__ void hyper_iter_kernel(const Hyper4 hw, const float *__restrict__ gc, const float *__restrict__ bc,
+                                  float *__restrict__ gate, float *__restrict__ hb, int n_ba, float beta, float sb, float cb)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n_ba * HYPER_TOTAL) return;
+    const int col = (int)(idx % HYPER_TOTAL);
+    const size_t i = (idx / HYPER_TOTAL) * HYPER_LD + col;
+    int li = 0, n = col;
+    while (n >= hw.l[li].dout) { n -= hw.l[li].dout; ++li; }
+    const float *wg = hw.l[li].gate_w + (size_t)n * 259;
+    const float *wb = hw.l[li].bias_w + (size_t)n * 259;
+    const float g = gc[i] + wg[0] * beta + wg[1] * sb + wg[2] * cb;
+    gate[i] = 1.0f / (1.0f + __expf(-g));
+    hb[i] = bc[i] + wb[0] * beta + wb[1] * sb + wb[2] * cb;
+}
+
+// concat1 (2 -> 512) + gate/bias + positional encoding; 128 threads per token, 4 columns each
+__global__ void embed_kernel(const float *__restrict__ x, const float *__restrict__ w1, const float *__restrict__ b1,
+                             const float *__restrict__ gate, const float *__restrict__ hb, const float *__restrict__ pe,
+                             bf16 *__restrict__ h, int n_tok_total, int tok_per_env, int T, int A)
+{
+    const int tok = blockIdx.x * (blockDim.x >> 7) + (threadIdx.x >> 7);
+    if (tok >= n_tok_total) return;
+    const int c4 = (threadIdx.x & 127) * 4;
+    const int b = tok / tok_per_env;
+    const int within = tok - b * tok_per_env;
+    const int r = within / T, tau = within - r * T;
+    const int ba = b * A + (r % A);
+    const float x0 = x[2 * (size_t)tok], x1 = x[2 * (size_t)tok + 1];
+    const float4 g = *reinterpret_cast<const float4 *>(gate + (size_t)ba * HYPER_LD + c4);
+    const float4 hbv = *reinterpret_cast<const float4 *>(hb + (size_t)ba * HYPER_LD + c4);
+    const float4 p = *reinterpret_cast<const float4 *>(pe + (size_t)tau * 512 + c4);
+    const float4 bb = *reinterpret_cast<const float4 *>(b1 + c4);
+    const float4 wa = *reinterpret_cast<const float4 *>(w1 + 2 * c4);     // w1[c4][0], w1[c4][1], w1[c4+1][0], w1[c4+1][1]
+    const float4 wb = *reinterpret_cast<const float4 *>(w1 + 2 * c4 + 4);
+    const float v0 = (wa.x * x0 + wa.y * x1 + bb.x) * g.x + hbv.x + p.x;
+    const float v1 = (wa.z * x0 + wa.w * x1 + bb.y) * g.y + hbv.y + p.y;
+    const float v2 = (wb.x * x0 + wb.y * x1 + bb.z) * g.z + hbv.z + p.z;
+    const float v3 = (wb.z * x0 + wb.w * x1 + bb.w) * g.w + hbv.w + p.w;
+    uint2 o;
+    o.x = tc::pack_bf16(v0, v1); o.y = tc::pack_bf16(v2, v3);
+    *reinterpret_cast<uint2 *>(h + (size_t)tok * 512 + c4) = o;
+}
+
+// LayerNorm over 512 fp32 columns, one warp per row (eps 1e-5, biased variance like torch)
+__global__ void layernorm_kernel(const float *__restrict__ in, const float *__restrict__ g, const float *__restrict__ b,
+                                 bf16 *__restrict__ out, int rows)
+{
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float4 *p = reinterpret_cast<const float4 *>(in + (size_t)row * 512);
+    float4 v[4];
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i] = p[lane + 32 * i]; sum += v[i].x + v[i].y + v[i].z + v[i].w; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / 512.0f);
+    float sq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float a = v[i].x - mean, c = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
+        sq += a * a + c * c + d * d + e * e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.0f / 512.0f) + 1e-5f);
+    const float4 *g4 = reinterpret_cast<const float4 *>(g), *b4 = reinterpret_cast<const float4 *>(b);
+    uint2 *o2 = reinterpret_cast<uint2 *>(out + (size_t)row * 512);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 gg = __ldg(g4 + lane + 32 * i), bb = __ldg(b4 + lane + 32 * i);
+        uint2 o;
+        o.x = tc::pack_bf16((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y);
+        o.y = tc::pack_bf16((v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
+        o2[lane + 32 * i] = o;
+    }
+}
+
+// `linear` ConcatSquash 128 -> 2 on the concat4 output, then the DDIM update (diffusion.py:524-528).
+// 8 lanes per token (16 columns each), 4 tokens per warp.
+__global__ void tail_ddim_kernel(const bf16 *__restrict__ t4, const float *__restrict__ wl, const float *__restrict__ bl,
+                                 const float *__restrict__ gate, const float *__restrict__ hb, int tab_ld,
+                                 const float *__restrict__ x_t, float *__restrict__ x_next, float *__restrict__ eps_out,
+                                 int n_tok_total, int tok_per_env, int T, int A, float c1, float c2, float c3, float c4)
+{
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tok = gid >> 3, sub = gid & 7;
+    const bool ok = tok < n_tok_total;
+    float a0 = 0.0f, a1 = 0.0f;
+    if (ok) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(t4 + (size_t)tok * 128 + sub * 16);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint4 u = p[q];
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162 *>(&w[i]);
+                const int k = sub * 16 + q * 8 + 2 * i;
+                const float f0 = __bfloat162float(v.x), f1 = __bfloat162float(v.y);
+                a0 = fmaf(f0, __ldg(wl + k), a0); a0 = fmaf(f1, __ldg(wl + k + 1), a0);
+                a1 = fmaf(f0, __ldg(wl + 128 + k), a1); a1 = fmaf(f1, __ldg(wl + 128 + k + 1), a1);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+    if (ok && sub == 0) {
+        const int b = tok / tok_per_env;
+        const int r = (tok - b * tok_per_env) / T;
+        const int ba = b * A + (r % A);
+        const float *gp = gate + (size_t)ba * tab_ld, *hp = hb + (size_t)ba * tab_ld;
+        const float e0 = (a0 + bl[0]) * gp[0] + hp[0];
+        const float e1 = (a1 + bl[1]) * gp[1] + hp[1];
+        if (eps_out) { eps_out[2 * (size_t)tok] = e0; eps_out[2 * (size_t)tok + 1] = e1; }
+        if (x_next) {
+            const float x0 = x_t[2 * (size_t)tok], x1 = x_t[2 * (size_t)tok + 1];
+            const float p0 = (x0 - e0 * c1) / c2, p1 = (x1 - e1 * c1) / c2;   // x0_t
+            x_next[2 * (size_t)tok] = c3 * p0 + c4 * e0;
+            x_next[2 * (size_t)tok + 1] = c3 * p1 + c4 * e1;
+        }
+    }
+}
+
+// positions = cumsum_t(v) * dt + p0[a]   (single_integrator.py:321); one thread per (b, s, a, xy)
+__global__ void integrate_kernel(const float *__restrict__ vel, const float *__restrict__ p0, float *__restrict__ pos, int B, int S,
+                                 int A, int T, float dt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * S * A * 2) return;
+    const int c = i & 1;
+    const int a = (i >> 1) % A;
+    const int b = (i >> 1) / (A * S);
+    const size_t base = (size_t)(i >> 1) * T * 2 + c;
+    const float start = p0[((size_t)b * A + a) * 2 + c];
+    float acc = 0.0f;
+    for (int t = 0; t < T; ++t) {
+        acc += vel[base + 2 * t];
+        pos[base + 2 * t] = acc * dt + start;
+    }
+}
+
+} // namespace
+
+int snb_k_f32_to_bf16(const float *src, bf16 *dst, size_t n, cudaStream_t s)
+{
+    f32_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, dst, n);
+    snb_count_launch();
+    SNB_CUDA_TRY(cudaGetLastError());
+    return SNB_OK;
+}
+
+static Hyper4 make_h4(const HyperW *l4)
+{
+    Hyper4 h;
+    for (int i = 0; i < 4; ++i) h.l[i] = l4[i];
+    return h;
+}
+
+int snb_k_hyper_ctx(const HyperW *layers4, const float *ctx, float *gc, float *bc, int n_ba, cudaStream_t s)
+{
+    hyper_ctx_kernel<<<n_ba, 256, 0, s>>>(make_h4(layers4), ctx, gc, bc);
+    snb_count_launch();
+    SNB_CUDA_TRY(cudaGetLastError());
+    return SNB_OK;
+}
+
+int snb_k_hyper_iter(const HyperW *layers4, const float *gc, const float *bc, float *gate, float *hb, int n_ba, float beta, cudaStream_t s)
+{
+    const size_t n = (size_t)n_ba * HYPER_TOTAL;
+    hyper_iter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(make_h4(layers4), gc, bc, gate, hb, n_ba, beta, sinf(beta), cosf(beta));
+    snb_count_launch();
+    SNB_CUDA_TRY(cudaGetLastError());
+    return SNB_OK;
+}
+
+int snb_k_embed(const float *x, const float *w1, const float *b1, const float *gate, const float *hb, const float *pe, bf16 *h,
+                int n_tok_total, int tok_per_env, int T, int A, cudaStream_t s)
+{
+    embed_kernel<<<(n_tok_total + 1) / 2, 256, 0, s>>>(x, w1, b1, gate, hb, pe, h, n_tok_total, tok_per_env, T, A);
+    snb_count_launch();
+    SNB_CUDA_TRY(cudaGetLastError());
+    return SNB_OK;
+}
+
+int snb_k_layernorm(const float *in, const float *g, const float *b, bf16 *out, int rows, cudaStream_t s)
+{
+    layernorm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(in, g, b, out, rows);
+    snb_count_launch();
+    SNB_CUDA_TRY(cudaGetLastError());
+    return SNB_OK;
+}
+
+int snb_k_tail_ddim(const bf16 *t4, const float *wl, const float *bl, const float *gate, const float *hb, int tab_ld,
+                    const float *x_t, float *x_next, float *eps_out, int n_tok_total, int tok_per_env, int T, int A,
+                    float c1, float c2, float c3, float c4, cudaStream_t s)
+{
+    const long long threads = (long long)n_tok_total * 8;
+    tail_ddim_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(t4, wl, bl, gate, hb, tab_ld, x_t, x_next, eps_out, n_tok_total,
+                                                                       tok_per_env, T, A, c1, c2, c3, c4);
+    snb_count_launch();
+    SNB_CUDA_TRY(cudaGetLastError());
+    return SNB_OK;
+}
+
+int snb_k_integrate(const float *vel, const float *p0, float *pos, int B, int S, int A, int T, float dt, cudaStream_t s)
+{
+    const int n = B * S * A * 2;
+    integrate_kernel<<<(n + 255) / 256, 256, 0, s>>>(vel, p0, pos, B, S, A, T, dt);
+    snb_count_launch();
+    SNB_CUDA_TRY(cudaGetLastError());
+    return SNB_OK;
+}
