@@ -1,0 +1,387 @@
+"""bench.py -- env-steps/s of the hot path on N B200s of one node (contract: see the task statement / DESIGN.md).
+
+Workload at every N (weak scaling, 1024 envs per GPU): BASELINE.json's metric configuration
+  "1024 x 10-human scenes w/ 20-step JMID denoise"  =  configs[1] (CrowdSimPlus ORCA step, 1024 envs x 10 humans)
+  + per env-step one JMID prediction as in configs[3] (10 humans x 20 samples x 8 steps = 1600 tokens, 20 DDIM
+  iterations, reference cross-sample attention), which is what SICNavAcados.predict does on every step
+  (sicnav_acados.py:1641-1644).
+One "step" = one CrowdSimPlus.step of all envs (snb_env_step) + one batched JMID denoise + integration.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  torchrun ... bench.py --gpus N ...          (N > 1: one rank per GPU, NCCL only for barrier / max / metric gather)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "safe-interactive-crowdnav_b200"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "env-steps/s, 1024x10-human scenes w/ 20-step JMID denoise"
+UNIT = "env-steps/s"
+
+ENV_CFG = """
+[env]
+time_limit = 30
+time_step = 0.25
+val_size = 100
+test_size = 500
+randomize_attributes = true
+[sim]
+train_val_sim = circle_crossing
+test_sim = circle_crossing
+starts_moving = 10
+square_width = 5
+circle_radius = 4.0
+rect_width = 1.75
+rect_height = 4
+human_num = {H}
+[humans]
+visible = true
+policy = orca
+radius = 0.3
+sensor = coordinates
+safety_space = 0.05
+v_pref = 1.5
+[robot]
+visible = true
+policy = linear
+radius = 0.25
+v_pref = 1.0
+sensor = coordinates
+[reward]
+success_reward = 1
+collision_penalty = -0.25
+freezing_penalty = -0.125
+discomfort_dist = 0.2
+discomfort_penalty_factor = 0.5
+"""
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], src="measured")
+    except Exception:
+        return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(smax) if smax else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def make_weights():
+    import jmid_oracle as JO
+    return JO.make_random_weights(5)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import configparser
+    from snb import _capi
+    from snb.env import CrowdSimPlusBatch
+    from snb.jmid import JmidDenoiser
+
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    B, H, S, A, T, NS = args.envs, args.humans, args.samples, args.humans, 8, args.denoise_steps
+
+    # ---- synthetic scenes: env b of rank r is the reference's test case r*B + b (seed 1000 + case) ----
+    cfg = configparser.RawConfigParser()
+    cfg.read_string(ENV_CFG.format(H=H))
+    env = CrowdSimPlusBatch(B, dev)
+    env.configure(cfg)
+    env.freeze_done = False                      # steady-state throughput: every env steps every iteration
+    env.reset('test', test_cases=(rank * B + np.arange(B)) % 500)
+    den = JmidDenoiser(make_weights(), max_envs=B, A=A, S=S, T=T, joint=True, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ctx = torch.randn(B, A, 256, device=dev, generator=gen)          # synthetic context (encoder = SURVEY 8f n1, not yet on device)
+    total = args.warmup + args.steps
+    xT = [torch.randn(B, S * A, T, 2, device=dev, generator=gen) for _ in range(min(total, 4))]
+    vel = torch.empty(B, S, A, T, 2, device=dev)
+    st = env.state
+
+    def robot_action():                          # stand-in robot policy (Linear): the Acados MPC is CPU code, out of scope
+        d = torch.stack([st.rgx - st.rpx, st.rgy - st.rpy], 1)
+        return (d / d.norm(dim=1, keepdim=True).clamp_min(1e-9) * env.robot_v_pref).contiguous()
+
+    def step(i):
+        env.step(robot_action())
+        den.denoise(ctx, xT[i % len(xT)], n_steps=NS, out=vel)
+        p0 = torch.stack([st.px, st.py], -1).float().contiguous()
+        return den.integrate(vel, p0)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        pos = step(args.warmup + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _capi.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----
+    h_ctx = torch.randn(B, A, 256).pin_memory(); h_xT = torch.randn(B, S * A, T, 2).pin_memory()
+    h_act = torch.zeros(B, 2, dtype=torch.float64).pin_memory()
+    h_act[:, 1] = env.robot_v_pref
+
+    def step_e2e():
+        ob, reward, done, flags = env.step_host(h_act.numpy())               # H2D action, D2H observation/reward/flags
+        pos_h = den.predict_host(h_ctx.numpy(), h_xT.numpy(), ob[:, :, :2].astype(np.float32), n_steps=NS)   # H2D ctx,x_T,p0; D2H pos
+        return ob, pos_h
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_e2e()
+    barrier()
+    ke = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(ke):
+        ob, pos_h = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * ke / e2e_s
+    h2d = h_act.numel() * 8 + h_ctx.numel() * 4 + h_xT.numel() * 4 + B * A * 2 * 4
+    d2h = ob.nbytes + B * 8 + B + B * 4 + pos_h.nbytes
+
+    # ---- roofline of the dominant kernels, timed live with CUDA events on the launching stream ----
+    pk = peaks()
+    roof, roof_other = kernel_rooflines(den, dev, pk, B, A, S, T, NS, ms / args.steps)
+
+    # ---- end-of-episode metric gather (the only collective of the path) ----
+    if dist is not None:
+        metrics = torch.stack([env.reward.float(), env.dmin.float(), env.flags.float()], 1)
+        gathered = [torch.empty_like(metrics) for _ in range(world)]
+        dist.all_gather(gathered, metrics)
+
+    if rank == 0:
+        cpu = cpu_baseline(H, S, NS, sample_envs=args.cpu_sample_envs)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 tensor-core GEMM/attention with fp32 accumulation (denoiser); f32 ORCA as in RVO2 on f64 state (crowd step)",
+            "data": "synthetic: seeded circle-crossing scenes (reference generator, seeds 1000+b), seeded random denoiser "
+                    "weights of the reference architecture, N(0,1) context and x_T",
+            "config": {"workload": f"configs[1]+configs[3]: CrowdSimPlus ORCA step {B} envs x {H} humans + JMID {S} samples x {NS} DDIM "
+                                   f"iterations per env-step ({A * S * T} tokens/env, cross-sample attention), per GPU",
+                       "envs_per_gpu": B, "humans": H, "samples": S, "denoise_steps": NS, "tokens_per_env": A * S * T,
+                       "l2_policy": "inputs larger than L2: activations of one step exceed 126 MB; x_T rotates over 4 buffers",
+                       "context": "synthetic N(0,1) (context encoder not yet on device)",
+                       "robot_policy": "Linear stand-in (MPC solve is CPU code outside the path)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": ke},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof, "roofline_other": roof_other,
+            "cpu_baseline": cpu,
+            "bound_note": "at sustained bf16 peak the reference semantics (S=20 cross-sample attention) bound sim+JMID at "
+                          f"{pk['tf_sustained'] * 1e12 / (den.flops_per_iter() * NS):.0f} env-steps/s per GPU (BASELINE.md section 3)",
+        }
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def kernel_rooflines(den, dev, pk, B, A, S, T, NS, ms_per_step):
+    """Average launch duration of the attention kernel and of the largest GEMM at the shapes the step uses (one chunk
+    of 16 envs), CUDA events on the launching stream, after warm-up."""
+    from snb import _capi
+    chunk = min(B, int(os.environ.get("SNB_JMID_CHUNK", 16)))
+    N = A * S * T
+    M = chunk * N
+    qkv = torch.randn(chunk, N, 1536, device=dev).bfloat16()
+    out = torch.empty(M, 512, device=dev, dtype=torch.bfloat16)
+    flush = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32)   # 256 MB > L2
+
+    def timeit(fn, reps=10):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+
+    t_attn = timeit(lambda: _capi.check(_capi.lib.snb_jmid_attention(_capi.ptr(qkv), _capi.ptr(out), chunk, N, _capi.stream_ptr()), "attn"))
+    fl_attn = 4.0 * N * N * 512 * chunk
+    Aa = torch.randn(M, 512, device=dev).bfloat16(); W = torch.randn(1536, 512, device=dev).bfloat16()
+    bias = torch.zeros(1536, device=dev); o2 = torch.empty(M, 1536, device=dev, dtype=torch.bfloat16)
+    t_gemm = timeit(lambda: _capi.check(_capi.lib.snb_jmid_gemm_bf16(_capi.ptr(Aa), _capi.ptr(W), _capi.ptr(bias), None, _capi.ptr(o2), M,
+                                                                    1536, 512, 0, _capi.stream_ptr()), "gemm"))
+    fl_gemm = 2.0 * M * 1536 * 512
+    peak = pk["tf_burst"]
+    n_chunks = (B + chunk - 1) // chunk
+    attn_share = t_attn * 3 * NS * n_chunks / ms_per_step
+    roof = {"kernel": "attn_fwd_kernel (flash attention, tcgen05 SS + TS, TMEM S/P/O)", "bound": "tensor",
+            "achieved": fl_attn / (t_attn * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+            "frac": fl_attn / (t_attn * 1e-3) / 1e12 / peak, "traffic": None, "peak_source": f"{pk['src']} (burst: kernel timed alone)",
+            "flops_per_launch": fl_attn, "avg_launch_ms": t_attn, "launches_per_step": 3 * NS * n_chunks,
+            "share_of_step": attn_share, "shape": f"{chunk} envs x 4 heads x {N} tokens x 128"}
+    other = [{"kernel": "gemm_bf16_tn_kernel<256,bias> (QKV projection, tcgen05 + TMA, persistent)", "bound": "tensor",
+              "achieved": fl_gemm / (t_gemm * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+              "frac": fl_gemm / (t_gemm * 1e-3) / 1e12 / peak, "traffic": None, "avg_launch_ms": t_gemm,
+              "shape": f"M={M} N=1536 K=512"},
+             {"kernel": "whole step (all kernels)", "bound": "tensor", "achieved": den.flops_per_iter() * NS * B / (ms_per_step * 1e-3) / 1e12,
+              "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+              "frac": den.flops_per_iter() * NS * B / (ms_per_step * 1e-3) / 1e12 / pk["tf_sustained"],
+              "peak_source": f"{pk['src']} (sustained: timed inside a long step)"}]
+    return roof, other
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_step_sample(H, S, NS, sample_envs, threads):
+    """The CPU restatement of the same step on a bounded sample: ORCA step of `sample_envs` envs (C oracle, pthreads) +
+    JMID denoise of the same envs (torch CPU oracle).  Returns seconds."""
+    import jmid_oracle as JO
+    import oracle_lib as ol
+    torch.set_num_threads(threads)
+    rng = np.random.default_rng(0)
+    env = ol.EnvArrays(sample_envs, H)
+    n = sample_envs * H
+    ang = rng.uniform(0, 2 * np.pi, n)
+    env.px[:] = 4 * np.cos(ang); env.py[:] = 4 * np.sin(ang); env.gx[:] = -env.px; env.gy[:] = -env.py
+    env.fgx[:] = env.gx; env.fgy[:] = env.gy; env.vpref[:] = rng.uniform(0.5, 1.5, n); env.radius[:] = 0.3
+    env.rpy[:] = -4.0; env.rgy[:] = 4.0
+    pcfg, rcfg, door = ol.default_policy_cfg("orca"), ol.default_reward_cfg(), ol.DoorCfg(enabled=0)
+    w = cpu_step_sample.w if hasattr(cpu_step_sample, "w") else make_weights()
+    cpu_step_sample.w = w
+    g = torch.Generator().manual_seed(0)
+    ctx = torch.randn(sample_envs, H, 256, generator=g); xT = torch.randn(sample_envs, S * H, 8, 2, generator=g)
+    t0 = time.perf_counter()
+    ol.env_step(pcfg, door, rcfg, env, np.tile([0.0, 1.0], (sample_envs, 1)), n_threads=threads)
+    with torch.no_grad():
+        for b in range(sample_envs):
+            v = JO.sample(w, ctx[b], xT[b], step=NS, joint=True)
+            JO.integrate(v, torch.zeros(H, 2))
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(H, S, NS, sample_envs=4):
+    threads = os.cpu_count() or 1
+    cpu_step_sample(H, S, NS, 1, threads)          # warm-up (first torch CPU call pages in MKL kernels)
+    dt = cpu_step_sample(H, S, NS, sample_envs, threads)
+    return {"value": sample_envs / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{sample_envs} of the 1024 envs: ORCA step (oracle/crowd_oracle.c) + JMID {S}x{NS} denoise (oracle/jmid_oracle.py, "
+                      f"torch CPU fp32), {dt:.1f} s",
+            "note": "the reference is pure Python and is not present on the GPU box; oracle = its CPU restatement pinned to it by tests/golden"}
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm on the host cores (oracle port), same metric / config; each step is a
+    bounded sample of the workload (sample_envs of the 1024 envs)."""
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return
+    H, S, NS = args.humans, args.samples, args.denoise_steps
+    threads = os.cpu_count() or 1
+    se = args.cpu_sample_envs
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_step_sample(H, S, NS, 1, threads)
+    ts = [cpu_step_sample(H, S, NS, se, threads) for _ in range(args.steps)]
+    dt = float(np.sum(ts))
+    value = se * args.steps / dt
+    sample = (f"each step = {se} of the {args.envs} envs: ORCA step (C oracle, {threads} threads) + JMID {S} samples x {NS} DDIM "
+              f"iterations (torch CPU fp32 oracle)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (CPU)",
+        "data": "synthetic (same generator family as the GPU arm)",
+        "config": {"workload": f"configs[1]+configs[3]: ORCA step + JMID {S}x{NS} per env-step, {args.envs} envs x {H} humans; bounded sample",
+                   "envs_per_gpu": args.envs, "humans": H, "samples": S, "denoise_steps": NS},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=1024, help="environments per GPU")
+    ap.add_argument("--humans", type=int, default=10)
+    ap.add_argument("--samples", type=int, default=20)
+    ap.add_argument("--denoise-steps", type=int, default=20)
+    ap.add_argument("--cpu-sample-envs", type=int, default=4)
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

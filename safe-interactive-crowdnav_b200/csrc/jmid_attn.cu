@@ -151,6 +151,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
             const int st = j & 1;
             const uint32_t ph = (j >> 1) & 1;
             tc::mbar_wait(&s_full[st], ph);
+            __syncwarp();                 // reconverge before the .sync.aligned TMEM loads
             tc::tc_fence_after();
             const uint32_t s_addr = tmem_base + lane_addr + (st ? TM_S1 : TM_S0);
             float s[BKV];
@@ -173,12 +174,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
             }
             if (j == 0) {
                 m_used = bmax;
-            } else if ((bmax - m_used) * c > RESCALE_THRESHOLD) {
-                // refresh the running max: O and l are rescaled once the previous PV has landed
+            } else if (__any_sync(0xffffffffu, (bmax - m_used) * c > RESCALE_THRESHOLD)) {
+                // Refresh the running max.  The decision is WARP-uniform (tcgen05.ld/st are .sync.aligned and must be
+                // executed by all 32 lanes together); lanes whose own max did not grow rescale by exactly 1.
                 const int pst = (j - 1) & 1;
-                tc::mbar_wait(&pv_done[pst], ((j - 1) >> 1) & 1);
+                tc::mbar_wait(&pv_done[pst], ((j - 1) >> 1) & 1);     // O is stable once the previous PV has landed
+                __syncwarp();
                 tc::tc_fence_after();
-                const float f = exp2f((m_used - bmax) * c);
+                const float m_new = fmaxf(m_used, bmax);
+                const float f = exp2f((m_used - m_new) * c);
                 const uint32_t o_addr = tmem_base + lane_addr + TM_O;
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) {
@@ -190,7 +194,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
                     tc::tmem_st_32x32(o_addr + ch * 32, r);
                 }
                 l *= f;
-                m_used = bmax;
+                m_used = m_new;
             }
             const float mc = m_used * c;
             float sum = 0.0f;
@@ -214,6 +218,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
         // final: O / l -> global
         const int lst = (n_kv - 1) & 1;
         tc::mbar_wait(&pv_done[lst], ((n_kv - 1) >> 1) & 1);
+        __syncwarp();
         tc::tc_fence_after();
         const float inv_l = 1.0f / l;
         const int row = q0 + row_in_tile;

@@ -185,6 +185,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 ba = b * ep.A + (r % ep.A);
             }
             tc::mbar_wait(&tfull[acc], acc_phase);
+            __syncwarp();                 // reconverge before the .sync.aligned TMEM loads
             tc::tc_fence_after();
             const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
