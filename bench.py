@@ -282,7 +282,7 @@ def kernel_rooflines(den, dev, pk, B, A, S, T, NS, ms_per_step):
     fl_attn = 4.0 * N * N * 512 * chunk
     Aa = torch.randn(M, 512, device=dev).bfloat16(); W = torch.randn(1536, 512, device=dev).bfloat16()
     bias = torch.zeros(1536, device=dev); o2 = torch.empty(M, 1536, device=dev, dtype=torch.bfloat16)
-    t_gemm = timeit(lambda: _capi.check(_capi.lib.snb_jmid_gemm_bf16(_capi.ptr(Aa), _capi.ptr(W), _capi.ptr(bias), None, _capi.ptr(o2), M,
+    t_gemm = timeit(lambda: _capi.check(_capi.lib.snb_jmid_gemm_bf16(_capi.ptr(Aa), _capi.ptr(W), _capi.ptr(bias), _capi.ptr(o2), M,
                                                                     1536, 512, 0, _capi.stream_ptr()), "gemm"))
     fl_gemm = 2.0 * M * 1536 * 512
     peak = pk["tf_burst"]

@@ -197,14 +197,14 @@ int snb_jmid_integrate(const float *vel_dev, const float *p0_dev, float *pos_dev
 int snb_jmid_predict_host(SnbJmid *h, const float *ctx_host, const float *x_T_host, const float *p0_host,
                           float *pos_host, int32_t B, int32_t n_steps, float dt);
 /* Component-level entry points (parity tests and micro-benchmarks of the two tensor-core kernels):
- *   snb_jmid_gemm_bf16:  out[M,N] = A[M,K] * W[N,K]^T + bias[N] (+ReLU)   A, W bf16 device buffers; out bf16
- *                        (epi = 0 bias, 1 bias+ReLU) or fp32 with a bf16 residual [M,N] added (epi = 2)
+ *   snb_jmid_gemm_bf16:  out[M,N] = A[M,K] * W[N,K]^T + bias[N]; A, W bf16 device buffers (row-major, K contiguous);
+ *                        epi = 0: bf16 out, 1: ReLU then bf16 out, 2: fp32 out (the pre-LayerNorm form)
  *   snb_jmid_attention:  multi-head self-attention (4 heads x 128) over n_env independent unmasked sequences of
  *                        n_tok tokens; qkv [n_env, n_tok, 1536] bf16 (Q|K|V) -> out [n_env*n_tok, 512] bf16
  * (the torch call sites they replace: nn.Linear / nn.MultiheadAttention inside nn.TransformerEncoderLayer,
  *  models/diffusion.py:161-166) */
-int snb_jmid_gemm_bf16(const void *A_dev, const void *W_dev, const float *bias_dev, const void *resid_dev, void *out_dev,
-                       int32_t M, int32_t N, int32_t K, int32_t epi, void *stream);
+int snb_jmid_gemm_bf16(const void *A_dev, const void *W_dev, const float *bias_dev, void *out_dev, int32_t M, int32_t N,
+                       int32_t K, int32_t epi, void *stream);
 int snb_jmid_attention(const void *qkv_dev, void *out_dev, int32_t n_env, int32_t n_tok, void *stream);
 /* algorithmic FLOPs of one denoise iteration for one environment */
 double snb_jmid_flops_per_iter(int32_t A, int32_t S, int32_t T, int32_t joint);

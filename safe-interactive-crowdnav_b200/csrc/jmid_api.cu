@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <utility>
 #include <vector>
 
 #include "jmid_internal.h"
@@ -39,6 +40,12 @@ struct SnbJmid {
     bf16 *h, *y, *qkv, *att, *ff, *t3, *t4;
     float *pre, *xa, *xb, *gc, *bc, *gate, *hb;
     std::map<int, Plans> plans;
+    // CUDA graphs of one chunk's whole DDIM loop, keyed by (envs in chunk, n_steps); captured on second use
+    float *ctx_stage = nullptr;
+    std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
+    std::map<std::pair<int, int>, int> graph_uses;
+    int use_graphs = 1;
+    cudaStream_t own_stream = nullptr;
     // host-call staging
     float *d_ctx = nullptr, *d_xT = nullptr, *d_p0 = nullptr, *d_vel = nullptr, *d_pos = nullptr;
 };
@@ -82,13 +89,13 @@ int get_plans(SnbJmid *h, int n_env, Plans **out)
     p.M = n_env * h->N;
     int rc = 0;
     for (int l = 0; l < NL && !rc; ++l) {
-        rc = snb_gemm_plan(&p.qkv[l], h->h, h->L[l].wqkv, p.M, 3 * D, D);
-        if (!rc) rc = snb_gemm_plan(&p.out[l], h->att, h->L[l].wo, p.M, D, D);
-        if (!rc) rc = snb_gemm_plan(&p.ff1[l], h->y, h->L[l].w1, p.M, DFF, D);
-        if (!rc) rc = snb_gemm_plan(&p.ff2[l], h->ff, h->L[l].w2, p.M, D, DFF);
+        rc = snb_gemm_plan(&p.qkv[l], h->h, h->L[l].wqkv, h->qkv, 0, p.M, 3 * D, D);
+        if (!rc) rc = snb_gemm_plan(&p.out[l], h->att, h->L[l].wo, h->pre, 1, p.M, D, D);
+        if (!rc) rc = snb_gemm_plan(&p.ff1[l], h->y, h->L[l].w1, h->ff, 0, p.M, DFF, D);
+        if (!rc) rc = snb_gemm_plan(&p.ff2[l], h->ff, h->L[l].w2, h->pre, 1, p.M, D, DFF);
     }
-    if (!rc) rc = snb_gemm_plan(&p.c3, h->h, h->wc3, p.M, 256, D);
-    if (!rc) rc = snb_gemm_plan(&p.c4, h->t3, h->wc4, p.M, 128, 256);
+    if (!rc) rc = snb_gemm_plan(&p.c3, h->h, h->wc3, h->t3, 0, p.M, 256, D);
+    if (!rc) rc = snb_gemm_plan(&p.c4, h->t3, h->wc4, h->t4, 0, p.M, 128, 256);
     if (!rc && h->joint) rc = snb_attn_plan(&p.attn, h->qkv, n_env, h->N);
     if (rc) return rc;
     h->plans[n_env] = p;
@@ -107,28 +114,25 @@ int net_forward(SnbJmid *h, Plans *P, const float *x_in, float *x_next, float *e
     GemmEpi e;
     for (int l = 0; l < NL; ++l) {
         memset(&e, 0, sizeof(e));
-        e.bias = h->L[l].bqkv; e.out = h->qkv; e.ldo = 3 * D;
+        e.bias = h->L[l].bqkv;
         if ((rc = snb_gemm_launch(&P->qkv[l], EPI_BIAS_BF16, &e, h->num_sms, s))) return rc;
         if (h->joint) rc = snb_attn_launch(&P->attn, h->att, s);
         else rc = snb_attn_small_launch(h->qkv, h->att, M / h->T, h->T, s);
         if (rc) return rc;
-        memset(&e, 0, sizeof(e));
-        e.bias = h->L[l].bo; e.out = h->pre; e.ldo = D; e.resid = h->h; e.ldr = D;
-        if ((rc = snb_gemm_launch(&P->out[l], EPI_BIAS_RESID_F32, &e, h->num_sms, s))) return rc;
-        if ((rc = snb_k_layernorm(h->pre, h->L[l].n1w, h->L[l].n1b, h->y, M, s))) return rc;
-        memset(&e, 0, sizeof(e));
-        e.bias = h->L[l].b1; e.out = h->ff; e.ldo = DFF;
+        e.bias = h->L[l].bo;
+        if ((rc = snb_gemm_launch(&P->out[l], EPI_BIAS_F32, &e, h->num_sms, s))) return rc;
+        if ((rc = snb_k_layernorm(h->pre, h->h, h->L[l].n1w, h->L[l].n1b, h->y, M, s))) return rc;   // y = LN1(h + attn)
+        e.bias = h->L[l].b1;
         if ((rc = snb_gemm_launch(&P->ff1[l], EPI_BIAS_RELU_BF16, &e, h->num_sms, s))) return rc;
-        memset(&e, 0, sizeof(e));
-        e.bias = h->L[l].b2; e.out = h->pre; e.ldo = D; e.resid = h->y; e.ldr = D;
-        if ((rc = snb_gemm_launch(&P->ff2[l], EPI_BIAS_RESID_F32, &e, h->num_sms, s))) return rc;
-        if ((rc = snb_k_layernorm(h->pre, h->L[l].n2w, h->L[l].n2b, h->h, M, s))) return rc;
+        e.bias = h->L[l].b2;
+        if ((rc = snb_gemm_launch(&P->ff2[l], EPI_BIAS_F32, &e, h->num_sms, s))) return rc;
+        if ((rc = snb_k_layernorm(h->pre, h->y, h->L[l].n2w, h->L[l].n2b, h->h, M, s))) return rc;   // h = LN2(y + ff)
     }
     memset(&e, 0, sizeof(e));
-    e.bias = h->c3_b; e.out = h->t3; e.ldo = 256; e.gate = h->gate + 512; e.hbias = h->hb + 512; e.tab_ld = HYPER_LD;
+    e.bias = h->c3_b; e.gate = h->gate + 512; e.hbias = h->hb + 512; e.tab_ld = HYPER_LD;
     e.tok_per_env = h->N; e.T = h->T; e.A = h->A;
     if ((rc = snb_gemm_launch(&P->c3, EPI_CSL_BF16, &e, h->num_sms, s))) return rc;
-    e.bias = h->c4_b; e.out = h->t4; e.ldo = 128; e.gate = h->gate + 768; e.hbias = h->hb + 768;
+    e.bias = h->c4_b; e.gate = h->gate + 768; e.hbias = h->hb + 768;
     if ((rc = snb_gemm_launch(&P->c4, EPI_CSL_BF16, &e, h->num_sms, s))) return rc;
     // DDIM coefficients in fp32 like torch: (1 - ab).sqrt(), ab.sqrt(), ab_next.sqrt(), (1 - ab_next).sqrt()
     const float ab = h->alpha_bars[t], abn = h->alpha_bars[t_next];
@@ -214,7 +218,12 @@ extern "C" int snb_jmid_create(SnbJmid **out, const SnbJmidWeights *w, int32_t m
     TRY(dev_alloc(h, &h->bc, nba * HYPER_LD));
     TRY(dev_alloc(h, &h->gate, nba * HYPER_LD));
     TRY(dev_alloc(h, &h->hb, nba * HYPER_LD));
+    TRY(dev_alloc(h, &h->ctx_stage, nba * 256));
 #undef TRY
+    {
+        const char *ge = getenv("SNB_JMID_GRAPH");
+        h->use_graphs = ge ? atoi(ge) : 1;
+    }
     if (!rc) {
         cudaError_t e = cudaMemcpyAsync(h->betas, w->betas, sizeof(float) * 101, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaMemcpyAsync(h->alpha_bars, w->alpha_bars, sizeof(float) * 101, cudaMemcpyDeviceToHost, s);
@@ -229,32 +238,75 @@ extern "C" int snb_jmid_create(SnbJmid **out, const SnbJmidWeights *w, int32_t m
 extern "C" int snb_jmid_destroy(SnbJmid *h)
 {
     if (!h) return SNB_OK;
+    for (auto &g : h->graphs) cudaGraphExecDestroy(g.second);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (void *p : h->allocs) cudaFree(p);
     cudaFree(h->d_ctx); cudaFree(h->d_xT); cudaFree(h->d_p0); cudaFree(h->d_vel); cudaFree(h->d_pos);
     delete h;
     return SNB_OK;
 }
 
+namespace {
+// hyper_ctx + the whole DDIM loop for the chunk staged in h->ctx_stage / h->xa; the result ends in *result
+int chunk_sequence(SnbJmid *h, Plans *P, int n_steps, cudaStream_t s, float **result)
+{
+    const int stride = 100 / n_steps; // int(100 / step), diffusion.py:507
+    int rc = snb_k_hyper_ctx(h->hyper, h->ctx_stage, h->gc, h->bc, P->n_env * h->A, s);
+    if (rc) return rc;
+    float *cur = h->xa, *nxt = h->xb;
+    for (int t = 100; t > 0; t -= stride) {
+        if ((rc = net_forward(h, P, cur, nxt, nullptr, t, t - stride, s))) return rc;
+        float *tmp = cur; cur = nxt; nxt = tmp;
+    }
+    *result = cur;
+    return SNB_OK;
+}
+} // namespace
+
 extern "C" int snb_jmid_denoise(SnbJmid *h, const float *ctx, const float *x_T, float *out_vel, int32_t B, int32_t n_steps, void *stream)
 {
     SNB_REQUIRE(h && ctx && x_T && out_vel, SNB_EINVAL, "snb_jmid_denoise: NULL argument");
     SNB_REQUIRE(B >= 0 && n_steps >= 1 && n_steps <= 100, SNB_EINVAL, "snb_jmid_denoise: bad B / n_steps");
     cudaStream_t s = (cudaStream_t)stream;
-    const int stride = 100 / n_steps; // int(100 / step), diffusion.py:507
+    const int stride = 100 / n_steps;
+    const int n_iter = (100 + stride - 1) / stride;
     for (int e0 = 0; e0 < B; e0 += h->chunk_envs) {
         const int ne = (B - e0) < h->chunk_envs ? (B - e0) : h->chunk_envs;
         Plans *P = nullptr;
         int rc = get_plans(h, ne, &P);
         if (rc) return rc;
         const size_t M = (size_t)P->M;
-        if ((rc = snb_k_hyper_ctx(h->hyper, ctx + (size_t)e0 * h->A * 256, h->gc, h->bc, ne * h->A, s))) return rc;
+        SNB_CUDA_TRY(cudaMemcpyAsync(h->ctx_stage, ctx + (size_t)e0 * h->A * 256, (size_t)ne * h->A * 256 * sizeof(float), cudaMemcpyDeviceToDevice, s));
         SNB_CUDA_TRY(cudaMemcpyAsync(h->xa, x_T + (size_t)e0 * h->N * 2, M * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        float *cur = h->xa, *nxt = h->xb;
-        for (int t = 100; t > 0; t -= stride) {
-            if ((rc = net_forward(h, P, cur, nxt, nullptr, t, t - stride, s))) return rc;
-            float *tmp = cur; cur = nxt; nxt = tmp;
+        float *result = (n_iter & 1) ? h->xb : h->xa;
+        const std::pair<int, int> key(ne, n_steps);
+        auto git = h->graphs.find(key);
+        if (git != h->graphs.end()) {
+            SNB_CUDA_TRY(cudaGraphLaunch(git->second, s));
+            snb_count_launch(1 + n_iter * 26);   // kernels inside the replayed graph
+        } else if (h->use_graphs && s != nullptr && ++h->graph_uses[key] >= 2) {
+            // second use of this shape: capture the sequence once, then replay it for every later chunk
+            cudaGraph_t graph = nullptr;
+            SNB_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            float *res2 = nullptr;
+            rc = chunk_sequence(h, P, n_steps, s, &res2);
+            snb_count_launch(-(1 + n_iter * 26)); // launches recorded during capture did not execute
+            cudaError_t ce = cudaStreamEndCapture(s, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) { snb_set_error("snb_jmid_denoise: graph capture failed: %s", cudaGetErrorString(ce)); return SNB_ECUDA; }
+            cudaGraphExec_t exec = nullptr;
+            ce = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) { snb_set_error("snb_jmid_denoise: graph instantiate failed: %s", cudaGetErrorString(ce)); return SNB_ECUDA; }
+            h->graphs[key] = exec;
+            SNB_CUDA_TRY(cudaGraphLaunch(exec, s));
+            snb_count_launch(1 + n_iter * 26);
+        } else {
+            float *res2 = nullptr;
+            if ((rc = chunk_sequence(h, P, n_steps, s, &res2))) return rc;
+            result = res2;
         }
-        SNB_CUDA_TRY(cudaMemcpyAsync(out_vel + (size_t)e0 * h->N * 2, cur, M * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        SNB_CUDA_TRY(cudaMemcpyAsync(out_vel + (size_t)e0 * h->N * 2, result, M * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
     return SNB_OK;
 }
@@ -296,7 +348,8 @@ extern "C" int snb_jmid_predict_host(SnbJmid *h, const float *ctx_host, const fl
         SNB_CUDA_TRY(cudaMalloc(&h->d_vel, me * h->N * 2 * sizeof(float)));
         SNB_CUDA_TRY(cudaMalloc(&h->d_pos, me * h->N * 2 * sizeof(float)));
     }
-    cudaStream_t s = 0;
+    if (!h->own_stream) SNB_CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    cudaStream_t s = h->own_stream;
     SNB_CUDA_TRY(cudaMemcpyAsync(h->d_ctx, ctx_host, (size_t)B * h->A * 256 * sizeof(float), cudaMemcpyHostToDevice, s));
     SNB_CUDA_TRY(cudaMemcpyAsync(h->d_xT, x_T_host, (size_t)B * h->N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
     SNB_CUDA_TRY(cudaMemcpyAsync(h->d_p0, p0_host, (size_t)B * h->A * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -309,20 +362,20 @@ extern "C" int snb_jmid_predict_host(SnbJmid *h, const float *ctx_host, const fl
     return SNB_OK;
 }
 
-extern "C" int snb_jmid_gemm_bf16(const void *A, const void *W, const float *bias, const void *resid, void *out, int32_t M,
-                                  int32_t N, int32_t K, int32_t epi, void *stream)
+extern "C" int snb_jmid_gemm_bf16(const void *A, const void *W, const float *bias, void *out, int32_t M, int32_t N, int32_t K,
+                                  int32_t epi, void *stream)
 {
     SNB_REQUIRE(A && W && bias && out, SNB_EINVAL, "snb_jmid_gemm_bf16: NULL argument");
-    SNB_REQUIRE(epi >= 0 && epi <= 2 && (epi != 2 || resid), SNB_EINVAL, "snb_jmid_gemm_bf16: bad epilogue");
+    SNB_REQUIRE(epi >= 0 && epi <= 2, SNB_EINVAL, "snb_jmid_gemm_bf16: bad epilogue");
     int dev = 0, sms = 0;
     SNB_CUDA_TRY(cudaGetDevice(&dev));
     SNB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     GemmPlan p;
-    int rc = snb_gemm_plan(&p, (const bf16 *)A, (const bf16 *)W, M, N, K);
+    int rc = snb_gemm_plan(&p, (const bf16 *)A, (const bf16 *)W, out, epi == 2, M, N, K);
     if (rc) return rc;
     GemmEpi e;
     memset(&e, 0, sizeof(e));
-    e.bias = bias; e.out = out; e.ldo = N; e.resid = (const bf16 *)resid; e.ldr = N;
+    e.bias = bias;
     return snb_gemm_launch(&p, epi, &e, sms, (cudaStream_t)stream);
 }
 

@@ -182,7 +182,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
                 __syncwarp();
                 tc::tc_fence_after();
                 const float m_new = fmaxf(m_used, bmax);
-                const float f = exp2f((m_used - m_new) * c);
+                const float f = tc::ex2_approx((m_used - m_new) * c);
                 const uint32_t o_addr = tmem_base + lane_addr + TM_O;
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) {
@@ -203,8 +203,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
                 uint32_t pk[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const float p0 = exp2f(fmaf(s[ch * 64 + 2 * i], c, -mc));
-                    const float p1 = exp2f(fmaf(s[ch * 64 + 2 * i + 1], c, -mc));
+                    const float p0 = tc::ex2_approx(fmaf(s[ch * 64 + 2 * i], c, -mc));
+                    const float p1 = tc::ex2_approx(fmaf(s[ch * 64 + 2 * i + 1], c, -mc));
                     sum += p0 + p1;
                     pk[i] = tc::pack_bf16(p0, p1);
                 }

@@ -7,7 +7,8 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled tiles A[128x64], W[BNx64] into a 4-stage smem ring
 //   warp 1      MMA issuer:   one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) x4 per stage,
 //                             tcgen05.commit releases the smem stage / publishes the accumulator
-//   warps 2..5  epilogue:     tcgen05.ld 32 lanes x 32 columns -> bias / ReLU / residual / ConcatSquash gate -> global
+//   warps 2..5  epilogue:     tcgen05.ld (software pipelined) -> bias (smem) / ReLU / ConcatSquash gate -> 128B-swizzled
+//                             smem staging -> cp.async.bulk.tensor store (coalesced, asynchronous, clips the M tail)
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of
 // tile i+1; CTAs are persistent (grid = #SMs) and walk the tile list with N fastest so that concurrently running
 // CTAs share the same A rows in L2.
@@ -21,6 +22,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int GEMM_THREADS = 192;
+constexpr int STAGING_BYTES = 32 * 128; // per epilogue warp: 32 rows x 128 B (one swizzle atom wide)
 
 template <int BN> struct GemmCfg {
     static constexpr int STAGES = 4;
@@ -28,30 +30,33 @@ template <int BN> struct GemmCfg {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BN; // 512 or 256: both powers of two
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
+    static constexpr int OFF_BIAS = OFF_STAGING + 4 * STAGING_BYTES;
+    static constexpr int OFF_BARS = OFF_BIAS + BN * 4;
+    static constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024 /*align*/;
 };
 
+// one 32-column chunk of one accumulator row: + bias (+ReLU | ConcatSquash), result left in v[]
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const GemmEpi &ep, int row, int col0, bool row_ok, int ba)
+__device__ __forceinline__ void epilogue_math(const uint32_t (&acc)[32], float (&v)[32], const float *s_bias, const GemmEpi &ep,
+                                              int col0_global, int ba)
 {
-    float v[32];
-    const float4 *b4 = reinterpret_cast<const float4 *>(ep.bias + col0);
+    const float4 *b4 = reinterpret_cast<const float4 *>(s_bias);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float4 b = __ldg(b4 + j);
+        const float4 b = b4[j];
         v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
         v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
         v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
         v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
     }
-    if (!row_ok) return;
     if constexpr (EPI == EPI_BIAS_RELU_BF16) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
     }
     if constexpr (EPI == EPI_CSL_BF16) {
-        const float4 *g4 = reinterpret_cast<const float4 *>(ep.gate + (size_t)ba * ep.tab_ld + col0);
-        const float4 *h4 = reinterpret_cast<const float4 *>(ep.hbias + (size_t)ba * ep.tab_ld + col0);
+        const float4 *g4 = reinterpret_cast<const float4 *>(ep.gate + (size_t)ba * ep.tab_ld + col0_global);
+        const float4 *h4 = reinterpret_cast<const float4 *>(ep.hbias + (size_t)ba * ep.tab_ld + col0_global);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float4 g = __ldg(g4 + j), h = __ldg(h4 + j);
@@ -61,47 +66,24 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&acc)[32], const 
             v[4 * j + 3] = fmaf(v[4 * j + 3], g.w, h.w);
         }
     }
-    if constexpr (EPI == EPI_BIAS_RESID_F32) {
-        const uint4 *r4 = reinterpret_cast<const uint4 *>(ep.resid + (size_t)row * ep.ldr + col0);
-        float4 *o4 = reinterpret_cast<float4 *>(reinterpret_cast<float *>(ep.out) + (size_t)row * ep.ldo + col0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint4 r = __ldg(r4 + j);
-            const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162 *>(&w[q]);
-                v[8 * j + 2 * q + 0] += __bfloat162float(p.x);
-                v[8 * j + 2 * q + 1] += __bfloat162float(p.y);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    } else {
-        uint4 *o4 = reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(ep.out) + (size_t)row * ep.ldo + col0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = tc::pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-            o.y = tc::pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-            o.z = tc::pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-            o.w = tc::pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-            o4[j] = o;
-        }
-    }
 }
+
+// 16-byte chunk `c` (0..7) of row `r` (0..31) inside a 32 x 128 B staging tile with the TMA 128-byte swizzle
+__device__ __forceinline__ uint4 *staging_slot(uint8_t *stg, int r, int c) { return reinterpret_cast<uint4 *>(stg + r * 128 + ((c ^ (r & 7)) << 4)); }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmEpi ep,
-                    const int M, const int N, const int K)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const GemmEpi ep, const int M, const int N, const int K)
 {
     using Cfg = GemmCfg<BN>;
+    constexpr bool OUT_F32 = (EPI == EPI_BIAS_F32);
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::OFF_BARS);
     uint64_t *full = bars, *empty = bars + Cfg::STAGES, *tfull = bars + 2 * Cfg::STAGES, *tempty = bars + 2 * Cfg::STAGES + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * Cfg::STAGES + 4);
+    float *s_bias = reinterpret_cast<float *>(smem + Cfg::OFF_BIAS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (M + BM - 1) / BM, n_tiles = N / BN;
@@ -111,6 +93,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tmA);
         tc::prefetch_tmap(&tmB);
+        tc::prefetch_tmap(&tmC);
         for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { tc::mbar_init(&tfull[s], 1); tc::mbar_init(&tempty[s], 128); }
         tc::fence_barrier_init();
@@ -171,33 +154,89 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3; // TMEM lanes [32*quarter, 32*quarter + 32)
+        const int etid = (warp - 2) * 32 + lane;
+        uint8_t *stg = smem + Cfg::OFF_STAGING + quarter * STAGING_BYTES;
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
-            const int row = m0 + quarter * 32 + lane;
-            const bool row_ok = row < M;
+            const int row0 = m0 + quarter * 32;
             int ba = 0;
             if constexpr (EPI == EPI_CSL_BF16) {
+                int row = row0 + lane;
+                if (row >= M) row = M - 1;
                 const int b = row / ep.tok_per_env;
                 const int r = (row - b * ep.tok_per_env) / ep.T;
                 ba = b * ep.A + (r % ep.A);
             }
+            // this tile's bias slice -> smem (the previous tile's readers are past their last use: barrier below)
+            tc::named_bar_sync(1, 128);
+            for (int i = etid; i < BN; i += 128) s_bias[i] = __ldg(ep.bias + n0 + i);
+            tc::named_bar_sync(1, 128);
+
             tc::mbar_wait(&tfull[acc], acc_phase);
             __syncwarp();                 // reconverge before the .sync.aligned TMEM loads
             tc::tc_fence_after();
             const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
+            uint32_t ra[32], rb[32];
+            float v[32];
+            tc::tmem_ld_32x32(t_addr, ra);
+            if constexpr (OUT_F32) {
+                // fp32 output: one 32-column chunk = 128 B per row = one store unit
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tc::tmem_ld_32x32(t_addr + c * 32, r);
-                tc::tmem_ld_wait();
-                epilogue_chunk<EPI>(r, ep, row, n0 + c * 32, row_ok, ba);
+                for (int c = 0; c < BN / 32; c += 2) {
+                    tc::tmem_ld_wait();
+                    tc::tmem_ld_32x32(t_addr + (c + 1) * 32, rb);
+                    epilogue_math<EPI>(ra, v, s_bias + c * 32, ep, n0 + c * 32, ba);
+                    if (lane == 0) tc::tma_store_wait_read<0>();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) *staging_slot(stg, lane, j) = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+                    tc::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) { tc::tma_store_2d(&tmC, stg, n0 + c * 32, row0); tc::tma_store_commit(); }
+                    tc::tmem_ld_wait();
+                    if (c + 2 < BN / 32) tc::tmem_ld_32x32(t_addr + (c + 2) * 32, ra);
+                    epilogue_math<EPI>(rb, v, s_bias + (c + 1) * 32, ep, n0 + (c + 1) * 32, ba);
+                    if (lane == 0) tc::tma_store_wait_read<0>();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) *staging_slot(stg, lane, j) = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+                    tc::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) { tc::tma_store_2d(&tmC, stg, n0 + (c + 1) * 32, row0); tc::tma_store_commit(); }
+                }
+            } else {
+                // bf16 output: two 32-column chunks = 128 B per row = one store unit
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; c += 2) {
+                    tc::tmem_ld_wait();
+                    tc::tmem_ld_32x32(t_addr + (c + 1) * 32, rb);
+                    epilogue_math<EPI>(ra, v, s_bias + c * 32, ep, n0 + c * 32, ba);
+                    if (lane == 0) tc::tma_store_wait_read<0>();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *staging_slot(stg, lane, j) = make_uint4(tc::pack_bf16(v[8 * j], v[8 * j + 1]), tc::pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                                                 tc::pack_bf16(v[8 * j + 4], v[8 * j + 5]), tc::pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                    tc::tmem_ld_wait();
+                    if (c + 2 < BN / 32) tc::tmem_ld_32x32(t_addr + (c + 2) * 32, ra);
+                    epilogue_math<EPI>(rb, v, s_bias + (c + 1) * 32, ep, n0 + (c + 1) * 32, ba);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *staging_slot(stg, lane, 4 + j) = make_uint4(tc::pack_bf16(v[8 * j], v[8 * j + 1]), tc::pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                                                     tc::pack_bf16(v[8 * j + 4], v[8 * j + 5]), tc::pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                    tc::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) { tc::tma_store_2d(&tmC, stg, n0 + c * 32, row0); tc::tma_store_commit(); }
+                }
             }
+            // every TMEM load of this tile has completed (last tmem_ld_wait above): hand the accumulator back
             tc::tc_fence_before();
             tc::mbar_arrive(&tempty[acc]);
         }
+        if (lane == 0) tc::tma_store_wait<0>();
     }
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -231,9 +270,10 @@ int launch_t(const GemmPlan *p, const GemmEpi *ep, int num_sms, cudaStream_t str
         attr_err = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     });
     SNB_CUDA_TRY(attr_err);
+    SNB_REQUIRE((EPI == EPI_BIAS_F32) == (p->out_f32 != 0), SNB_EINVAL, "gemm: epilogue %d does not match the plan's output type", EPI);
     const int tiles = ((p->M + BM - 1) / BM) * (p->N / BN);
     const int grid = tiles < num_sms ? tiles : num_sms;
-    gemm_bf16_tn_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p->tmA, p->tmB, *ep, p->M, p->N, p->K);
+    gemm_bf16_tn_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p->tmA, p->tmB, p->tmC, *ep, p->M, p->N, p->K);
     snb_count_launch();
     SNB_CUDA_TRY(cudaGetLastError());
     return SNB_OK;
@@ -245,56 +285,56 @@ int launch_bn(const GemmPlan *p, int kind, const GemmEpi *ep, int num_sms, cudaS
     switch (kind) {
     case EPI_BIAS_BF16: return launch_t<BN, EPI_BIAS_BF16>(p, ep, num_sms, stream);
     case EPI_BIAS_RELU_BF16: return launch_t<BN, EPI_BIAS_RELU_BF16>(p, ep, num_sms, stream);
-    case EPI_BIAS_RESID_F32: return launch_t<BN, EPI_BIAS_RESID_F32>(p, ep, num_sms, stream);
+    case EPI_BIAS_F32: return launch_t<BN, EPI_BIAS_F32>(p, ep, num_sms, stream);
     case EPI_CSL_BF16: return launch_t<BN, EPI_CSL_BF16>(p, ep, num_sms, stream);
     }
     snb_set_error("gemm: unknown epilogue %d", kind);
     return SNB_EINVAL;
 }
 
+int make_tmap(CUtensorMap *out, CUtensorMapDataType dt, int elem_bytes, int rank, const void *ptr, const cuuint64_t *dims,
+              const cuuint32_t *box)
+{
+    EncodeTiledFn enc = get_encode();
+    SNB_REQUIRE(enc != nullptr, SNB_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    SNB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (dims[0] * elem_bytes) % 16 == 0, SNB_EINVAL, "tensor map: unaligned tensor");
+    cuuint64_t strides[2] = {dims[0] * elem_bytes, dims[0] * dims[1] * elem_bytes};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(out, dt, rank, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SNB_REQUIRE(r == CUDA_SUCCESS, SNB_ECUDA, "cuTensorMapEncodeTiled(rank %d) failed: %d", rank, (int)r);
+    return SNB_OK;
+}
+
 } // namespace
 
 int snb_make_tmap_2d(CUtensorMap *out, const void *ptr, uint64_t rows, uint64_t cols, uint32_t box_rows)
 {
-    EncodeTiledFn enc = get_encode();
-    SNB_REQUIRE(enc != nullptr, SNB_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    SNB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (cols * 2) % 16 == 0, SNB_EINVAL, "tensor map: unaligned matrix");
     const cuuint64_t dims[2] = {cols, rows};
-    const cuuint64_t strides[1] = {cols * 2};
     const cuuint32_t box[2] = {64, box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SNB_REQUIRE(r == CUDA_SUCCESS, SNB_ECUDA, "cuTensorMapEncodeTiled(2d %llux%llu) failed: %d", (unsigned long long)rows,
-                (unsigned long long)cols, (int)r);
-    return SNB_OK;
+    return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 2, ptr, dims, box);
 }
 
 int snb_make_tmap_3d(CUtensorMap *out, const void *ptr, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box_rows)
 {
-    EncodeTiledFn enc = get_encode();
-    SNB_REQUIRE(enc != nullptr, SNB_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    SNB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (d0 * 2) % 16 == 0, SNB_EINVAL, "tensor map: unaligned tensor");
     const cuuint64_t dims[3] = {d0, d1, d2};
-    const cuuint64_t strides[2] = {d0 * 2, d1 * d0 * 2};
     const cuuint32_t box[3] = {64, box_rows, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(ptr), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SNB_REQUIRE(r == CUDA_SUCCESS, SNB_ECUDA, "cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
-    return SNB_OK;
+    return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3, ptr, dims, box);
 }
 
-int snb_gemm_plan(GemmPlan *plan, const bf16 *A, const bf16 *W, int M, int N, int K)
+int snb_gemm_plan(GemmPlan *plan, const bf16 *A, const bf16 *W, void *out, int out_f32, int M, int N, int K)
 {
     SNB_REQUIRE(M > 0 && K % BK == 0 && N % 128 == 0, SNB_EUNSUPPORTED, "gemm: unsupported shape M=%d N=%d K=%d", M, N, K);
-    plan->M = M; plan->N = N; plan->K = K;
+    plan->M = M; plan->N = N; plan->K = K; plan->out_f32 = out_f32;
     plan->BN = (N % 256 == 0) ? 256 : 128;
     int rc = snb_make_tmap_2d(&plan->tmA, A, (uint64_t)M, (uint64_t)K, BM);
     if (rc) return rc;
-    return snb_make_tmap_2d(&plan->tmB, W, (uint64_t)N, (uint64_t)K, (uint32_t)plan->BN);
+    rc = snb_make_tmap_2d(&plan->tmB, W, (uint64_t)N, (uint64_t)K, (uint32_t)plan->BN);
+    if (rc) return rc;
+    // output [M, N]: store unit = 32 rows x 128 bytes
+    const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    const cuuint32_t box[2] = {out_f32 ? 32u : 64u, 32u};
+    return make_tmap(&plan->tmC, out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, out_f32 ? 4 : 2, 2, out, dims, box);
 }
 
 int snb_gemm_launch(const GemmPlan *plan, int epi_kind, const GemmEpi *epi, int num_sms, cudaStream_t stream)

@@ -19,16 +19,12 @@ int snb_make_tmap_3d(CUtensorMap *out, const void *ptr, uint64_t d2, uint64_t d1
 enum GemmEpiKind {
     EPI_BIAS_BF16 = 0,      // out_bf16 = acc + bias[n]
     EPI_BIAS_RELU_BF16 = 1, // out_bf16 = relu(acc + bias[n])
-    EPI_BIAS_RESID_F32 = 2, // out_f32  = acc + bias[n] + resid_bf16[m,n]
+    EPI_BIAS_F32 = 2,       // out_f32  = acc + bias[n]   (pre-LayerNorm; the residual is added by the LayerNorm kernel)
     EPI_CSL_BF16 = 3        // out_bf16 = (acc + bias[n]) * gate[ba(m),n] + hbias[ba(m),n]   (ConcatSquashLinear)
 };
 
 struct GemmEpi {
     const float *bias;      // [N]
-    void *out;              // [M, ldo]
-    int ldo;
-    const bf16 *resid;      // [M, ldr]
-    int ldr;
     const float *gate;      // [n_ba, tab_ld] already sigmoid()ed, pointing at this layer's first column
     const float *hbias;     // [n_ba, tab_ld]
     int tab_ld;
@@ -36,10 +32,10 @@ struct GemmEpi {
 };
 
 struct GemmPlan {
-    CUtensorMap tmA, tmB;
-    int M, N, K, BN;
+    CUtensorMap tmA, tmB, tmC; // tmC: output [M,N] (bf16 or fp32), written with TMA stores of 32 rows x 128 B
+    int M, N, K, BN, out_f32;
 };
-int snb_gemm_plan(GemmPlan *plan, const bf16 *A, const bf16 *W, int M, int N, int K);
+int snb_gemm_plan(GemmPlan *plan, const bf16 *A, const bf16 *W, void *out, int out_f32, int M, int N, int K);
 int snb_gemm_launch(const GemmPlan *plan, int epi_kind, const GemmEpi *epi, int num_sms, cudaStream_t stream);
 
 // ---- attention (jmid_attn.cu) ----
@@ -64,8 +60,8 @@ int snb_k_hyper_iter(const HyperW *layers4, const float *gc, const float *bc, fl
 // concat1 + positional encoding: h[m, 512] = (W1 x[m] + b1) * gate[ba, 0:512] + hb[ba, 0:512] + pe[tau]
 int snb_k_embed(const float *x, const float *w1, const float *b1, const float *gate, const float *hb, const float *pe, bf16 *h,
                 int n_tok_total, int tok_per_env, int T, int A, cudaStream_t s);
-// LayerNorm(512) of fp32 rows -> bf16
-int snb_k_layernorm(const float *in, const float *g, const float *b, bf16 *out, int rows, cudaStream_t s);
+// out_bf16 = LayerNorm(512)(in_f32 + resid_bf16)
+int snb_k_layernorm(const float *in, const bf16 *resid, const float *g, const float *b, bf16 *out, int rows, cudaStream_t s);
 // final ConcatSquash 128 -> 2 and the DDIM update of x_t (diffusion.py:524-528); eps_out optional
 int snb_k_tail_ddim(const bf16 *t4, const float *wl, const float *bl, const float *gate, const float *hb, int tab_ld,
                     const float *x_t, float *x_next, float *eps_out, int n_tok_total, int tok_per_env, int T, int A,

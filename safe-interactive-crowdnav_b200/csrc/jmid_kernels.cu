@@ -80,8 +80,8 @@ __global__ void embed_kernel(const float *__restrict__ x, const float *__restric
 }
 
 // LayerNorm over 512 fp32 columns, one warp per row (eps 1e-5, biased variance like torch)
-__global__ void layernorm_kernel(const float *__restrict__ in, const float *__restrict__ g, const float *__restrict__ b,
-                                 bf16 *__restrict__ out, int rows)
+__global__ void layernorm_kernel(const float *__restrict__ in, const bf16 *__restrict__ resid, const float *__restrict__ g,
+                                 const float *__restrict__ b, bf16 *__restrict__ out, int rows)
 {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -90,7 +90,15 @@ __global__ void layernorm_kernel(const float *__restrict__ in, const float *__re
     float4 v[4];
     float sum = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { v[i] = p[lane + 32 * i]; sum += v[i].x + v[i].y + v[i].z + v[i].w; }
+    const uint2 *rp = reinterpret_cast<const uint2 *>(resid + (size_t)row * 512);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[i] = p[lane + 32 * i];
+        const uint2 rr = rp[lane + 32 * i];
+        const __nv_bfloat162 r0 = *reinterpret_cast<const __nv_bfloat162 *>(&rr.x), r1 = *reinterpret_cast<const __nv_bfloat162 *>(&rr.y);
+        v[i].x += __bfloat162float(r0.x); v[i].y += __bfloat162float(r0.y); v[i].z += __bfloat162float(r1.x); v[i].w += __bfloat162float(r1.y);
+        sum += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float mean = sum * (1.0f / 512.0f);
@@ -222,9 +230,9 @@ int snb_k_embed(const float *x, const float *w1, const float *b1, const float *g
     return SNB_OK;
 }
 
-int snb_k_layernorm(const float *in, const float *g, const float *b, bf16 *out, int rows, cudaStream_t s)
+int snb_k_layernorm(const float *in, const bf16 *resid, const float *g, const float *b, bf16 *out, int rows, cudaStream_t s)
 {
-    layernorm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(in, g, b, out, rows);
+    layernorm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(in, resid, g, b, out, rows);
     snb_count_launch();
     SNB_CUDA_TRY(cudaGetLastError());
     return SNB_OK;

@@ -99,7 +99,7 @@ _proto("snb_jmid_eps", C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp], required=
 _proto("snb_jmid_integrate", C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, C.c_float, _vp], required=False)
 _proto("snb_jmid_predict_host", C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                            C.POINTER(C.c_float), _i32, _i32, C.c_float], required=False)
-_proto("snb_jmid_gemm_bf16", C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp], required=False)
+_proto("snb_jmid_gemm_bf16", C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp], required=False)
 _proto("snb_jmid_attention", C.c_int, [_vp, _vp, _i32, _i32, _vp], required=False)
 _proto("snb_jmid_flops_per_iter", _d, [_i32, _i32, _i32, _i32], required=False)
 
