@@ -259,7 +259,7 @@ def kernel_rooflines(den, dev, pk, B, A, S, T, NS, ms_per_step):
     """Average launch duration of the attention kernel and of the largest GEMM at the shapes the step uses (one chunk
     of 16 envs), CUDA events on the launching stream, after warm-up."""
     from snb import _capi
-    chunk = min(B, int(os.environ.get("SNB_JMID_CHUNK", 16)))
+    chunk = min(B, int(os.environ.get("SNB_JMID_CHUNK", 128)))
     N = A * S * T
     M = chunk * N
     qkv = torch.randn(chunk, N, 1536, device=dev).bfloat16()

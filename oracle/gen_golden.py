@@ -362,3 +362,106 @@ if __name__ == "__main__":
             gen_rollouts()
         if "jmid" in which:
             gen_jmid()
+
+
+# ------------------------------------------------------------------ full predictor (a13-a17, a22-a25)
+def gen_predictor():
+    """Runs the reference's own HumanTrajectoryForecasterSim (mid_sim_wrapper.py) on CPU with (a) the shipped JMID
+    checkpoint and (b) seeded synthetic encoder + denoiser weights written INTO the reference modules, recording the
+    histories, the cluster split, the encoder context, the injected noise and predict_ret_best's outputs."""
+    import yaml
+    import ref_predictor_shims as RPS
+    import jmid_oracle as JO
+    import predictor_oracle as PO
+    EasyDict = RPS.install()
+    from sicnav_diffusion.JMID import mid_sim_wrapper as W
+    REF = ref_shims.REF
+    cwd = os.getcwd()
+    os.chdir(REF)
+    out = {}
+
+    class S:
+        def __init__(self, x, y):
+            self.position = (x, y)
+
+    def build(H, num_draw, num_ret, step):
+        cfg = configparser.RawConfigParser()
+        cfg.read(REF_CFG)
+        cfg.set("sim", "human_num", str(H))
+        cfg.set("human_trajectory_forecaster", "num_samples", str(num_ret))
+        y = yaml.safe_load(open(os.path.join(REF, "sicnav_diffusion/JMID/test_time_configs/mid_jp.yaml")))
+        y.update(device="cpu", model_path=os.path.join(REF, y["model_path"]), num_samples=num_draw, step_size=step)
+        return W.HumanTrajectoryForecasterSim(cfg, EasyDict(y))
+
+    def run(tag, f, H, rng, spread, synthetic):
+        if synthetic:
+            ew = PO.make_random_encoder_weights(seed=9)
+            md = f.mid_model.registrar.model_dict
+            with torch.no_grad():
+                for k, v in ew.items():
+                    mod, pname = k.rsplit("/", 1)
+                    dict(md[mod].named_parameters())[pname].copy_(v)
+                dw = JO.make_random_weights(5)
+                sd = f.mid_model.model.vel_predictor.state_dict()
+                for k, v in dw.items():
+                    sd[k].copy_(v)
+        p0 = rng.uniform(-spread, spread, (H, 2)); v0 = rng.uniform(-0.8, 0.8, (H, 2))
+        rp = np.array([0.0, -spread * 0.6]); rv = np.array([0.1, 0.9])
+        acc = rng.uniform(-0.3, 0.3, (H, 2))
+        for i in range(H):
+            f.prev_states[i].clear()
+        f.prev_robot_states.clear()
+        for k in range(8):          # more than 6 frames: the ring keeps the last 6
+            t = 0.25 * k
+            f.update_state_hists(S(*(rp + rv * t)), [S(*(p0[i] + v0[i] * t + 0.5 * acc[i] * t * t)) for i in range(H)], t)
+        rec = {}
+        vp = f.mid_model.model.vel_predictor
+        orig_sample = vp.sample_sicnav_inference
+        orig_randn = torch.randn
+
+        def sample_hook(num_points, context, sample, bestof, **kw):
+            rec["ctx"] = context.detach().clone()
+            g = torch.Generator().manual_seed(4321)
+
+            def fake_randn(*size, **k2):
+                size = size[0] if len(size) == 1 and isinstance(size[0], (list, tuple, torch.Size)) else size
+                t_ = orig_randn(*size, generator=g)
+                if "xT" not in rec:
+                    rec["xT"] = t_.clone()
+                return t_
+            torch.randn = fake_randn
+            try:
+                return orig_sample(num_points, context, sample, bestof, **kw)
+            finally:
+                torch.randn = orig_randn
+        vp.sample_sicnav_inference = sample_hook
+        env_, poses, ids_in, ids_out, cv = f.convert_to_mid_state_env(f.prev_states, f.prev_robot_states)
+        fc, lw = f.predict_ret_best()
+        vp.sample_sicnav_inference = orig_sample
+        out[f"{tag}_hist"] = np.array([s_ for s_ in f.prev_states], np.float64)          # [H,6,3]
+        out[f"{tag}_robot_hist"] = np.array(f.prev_robot_states[-6:], np.float64)       # [6,3]
+        out[f"{tag}_ids_in"] = np.array(ids_in, np.int64); out[f"{tag}_ids_out"] = np.array(ids_out, np.int64)
+        out[f"{tag}_ctx"] = rec["ctx"].numpy(); out[f"{tag}_xT"] = rec["xT"].numpy()
+        out[f"{tag}_forecasts"] = fc; out[f"{tag}_logw"] = lw
+        out[f"{tag}_cfg"] = np.array([H, f.mid_model.num_samples, f.num_ret_samples, f.mid_model.config.step_size])
+        print(f"predictor {tag}: H={H} in={list(ids_in)} out={list(ids_out)} ctx={tuple(rec['ctx'].shape)} fc={fc.shape}")
+
+    with torch.no_grad():
+        rng = np.random.default_rng(2024)
+        f = build(5, 20, 20, 20)
+        run("ckpt_h5", f, 5, rng, 1.5, False)
+        run("ckpt_h5_sparse", f, 5, rng, 4.0, False)
+        run("rand_h5", f, 5, rng, 1.5, True)
+        run("rand_h5_sparse", f, 5, rng, 4.0, True)
+        f = build(10, 20, 20, 4)
+        run("rand_h10", f, 10, rng, 2.5, True)
+        f = build(4, 20, 8, 5)            # num_ret < drawn: KDE top-k branch (get_most_likely_samples)
+        run("rand_h4_kde", f, 4, rng, 1.2, True)
+        run("ckpt_h4_kde", build(4, 20, 8, 5), 4, rng, 1.2, False)
+    os.chdir(cwd)
+    np.savez_compressed(os.path.join(OUT, "predictor_cases.npz"), enc_seed=9, ddpm_seed=5, **out)
+
+
+if "predictor" in sys.argv[1:]:
+    with np.errstate(all="ignore"):
+        gen_predictor()

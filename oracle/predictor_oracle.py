@@ -1,0 +1,220 @@
+"""oracle/predictor_oracle.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+CPU restatement (numpy + torch tensor algebra) of the JMID predictor around the denoiser, i.e. everything
+HumanTrajectoryForecasterSim.predict_ret_best does (paths relative to the reference root):
+  * history -> per-node state (finite differences), 3 m clustering, constant-velocity fall-back
+      sicnav_diffusion/JMID/mid_sim_wrapper.py:244-437, MID/environment/data_utils.py:24-37
+  * scene graph + edge scaling, standardisation, neighbour batches
+      MID/environment/scene_graph.py:111-225, 280-313; MID/dataset/preprocessing.py:428-620
+  * Trajectron context encoder (history LSTM, per-edge-type LSTM, additive attention)
+      MID/models/encoders/mgcvae.py:505-880, components/additive_attention.py:6-47
+  * KDE top-k (get_most_likely_samples, mid_sim_wrapper.py:14-169), scatter + current pose (:482-509)
+  * the MPC ingest of sicnav_diffusion/policy/sicnav_acados.py:1645-1667
+Pinned against the reference's own stack run on CPU in the build container (tests/golden/predictor_cases.npz, made by
+oracle/gen_golden.py predictor) with the shipped checkpoint and with seeded synthetic weights.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+"""
+import math
+
+import numpy as np
+import torch
+
+import jmid_oracle as JO
+
+ENC_KEYS = {
+    "PEDESTRIAN/node_history_encoder": 6,
+    "PEDESTRIAN->PEDESTRIAN/edge_encoder": 12,
+    "PEDESTRIAN->JRDB_ROBOT/edge_encoder": 12,
+}
+STD = np.array([3.0, 3.0, 2.0, 2.0, 1.0, 1.0])   # position std is replaced by the attention radius (preprocessing.py:477-478)
+
+
+def make_random_encoder_weights(seed=9):
+    """Seeded synthetic encoder weights with the names of `checkpoint["encoder"]`."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    w = {}
+    b = 1.0 / math.sqrt(128)
+    for mod, din in ENC_KEYS.items():
+        w[f"{mod}/weight_ih_l0"] = rng.uniform(-b, b, (512, din))
+        w[f"{mod}/weight_hh_l0"] = rng.uniform(-b, b, (512, 128))
+        w[f"{mod}/bias_ih_l0"] = rng.uniform(-b, b, (512,))
+        w[f"{mod}/bias_hh_l0"] = rng.uniform(-b, b, (512,))
+    for n, s in (("w1.weight", (128, 128)), ("w2.weight", (128, 128)), ("v.weight", (1, 128))):
+        w[f"PEDESTRIAN/edge_influence_encoder/{n}"] = rng.uniform(-b, b, s)
+    return {k: torch.from_numpy(np.asarray(v, np.float32)) for k, v in w.items()}
+
+
+def derivative_of(x, dt):
+    """data_utils.derivative_of: first difference duplicated at the front, divided by dt."""
+    return np.ediff1d(x, to_begin=(x[1] - x[0])) / dt
+
+
+def node_states(pos, dt):
+    """pos [Th,2] -> [Th,6] = x,y,vx,vy,ax,ay (mid_sim_wrapper.py:376-391)."""
+    x, y = pos[:, 0], pos[:, 1]
+    vx, vy = derivative_of(x, dt), derivative_of(y, dt)
+    ax, ay = derivative_of(vx, dt), derivative_of(vy, dt)
+    return np.stack([x, y, vx, vy, ax, ay], 1)
+
+
+def cluster_split(hist, robot_hist, radius=3.0):
+    """mid_sim_wrapper.py:322-355.  hist [H,Th,3], robot_hist [Th,3] -> (in_cluster bool [H+1], order) with index 0 = robot
+    (track id -1) and index 1+i = human i, exactly the sorted-by-track-id order of the reference."""
+    positions = np.concatenate([robot_hist[-1:, :2], hist[:, -1, :2]], 0)
+    sq = np.square(positions[:, None] - positions[None, :])
+    dists = np.sqrt(np.sum(sq, axis=2))
+    mask = dists < radius
+    cluster_means = (mask @ positions) / mask.sum(axis=1, keepdims=True)
+    robot_dist = np.linalg.norm(cluster_means - positions[0], axis=1)
+    chosen = int(np.argmin(robot_dist[1:]) + 1)
+    return mask[chosen]
+
+
+def edge_scaling(pos3, is_ped, radius=3.0):
+    """TemporalSceneGraph.create_from_temp_scene_dict + calculate_edge_scaling at the current frame for the shipped
+    filters add=[.25,.5,.75,1], remove=[1,0] (scene_graph.py:111-225).  pos3 [3,n,2] = frames t-2..t."""
+    n = pos3.shape[1]
+    adj = np.zeros((3, n, n))
+    for k in range(3):
+        d = np.sqrt(((pos3[k][:, None] - pos3[k][None, :]) ** 2).sum(-1))
+        a = (d <= radius).astype(np.float64)
+        np.fill_diagonal(a, 0)
+        adj[k] = a
+    new_edges = np.minimum(0.25 * adj[2] + 0.5 * adj[1] + 0.75 * adj[0], 1.0)
+    new_edges[adj[2] == 0] = 0
+    return new_edges        # removal filter [1, 0] leaves the current frame unchanged
+
+
+def encoder_inputs(hist, robot_hist, dt=0.25, radius=3.0):
+    """Everything up to the encoder: returns dict(in_cluster [H] bool, ped_ids (in-cluster humans, ascending),
+    x_st [A,6,6], nb_ped [A,6,6], nb_rob [A,6,6], edge_mask [A], p0 [A,2], cv {h: [T,2]} filled by the caller)."""
+    H, Th, _ = hist.shape
+    inc = cluster_split(hist, robot_hist, radius)
+    nodes = [i for i in range(H + 1) if inc[i]]             # 0 = robot
+    states = {}
+    for i in nodes:
+        p = robot_hist[-Th:, :2] if i == 0 else hist[i - 1, :, :2]
+        states[i] = node_states(p, dt)
+    pos3 = np.stack([np.stack([states[i][Th - 3 + k, :2] for i in nodes], 0) for k in range(3)], 0)
+    es = edge_scaling(pos3, None, radius)
+    ped_nodes = [i for i in nodes if i != 0]
+    x_st, nb_ped, nb_rob, emask, p0 = [], [], [], [], []
+    for a, i in enumerate(nodes):
+        if i == 0:
+            continue
+        x = states[i]
+        rel = np.zeros(6); rel[0:2] = x[-1, 0:2]
+        x_st.append((x - rel) / STD)
+        conn = es[a] > 1e-2                                   # SceneGraph.get_connection_mask
+        sp, sr = np.zeros((Th, 6)), np.zeros((Th, 6))
+        for b_, j in enumerate(nodes):
+            if not conn[b_]:
+                continue
+            nst = (states[j] - x[-1][None, :]) / STD         # relative to the node's CURRENT full state (:541-551)
+            if j == 0:
+                sr += nst
+            else:
+                sp += nst
+        nb_ped.append(sp); nb_rob.append(sr)
+        emask.append(min(float(es[a][conn].sum()), 1.0))     # clamp(sum over ALL neighbours, 1) for every edge type (q5)
+        p0.append(x[-1, 0:2])
+    return dict(in_cluster=inc[1:], ped_ids=[i - 1 for i in ped_nodes], x_st=np.array(x_st), nb_ped=np.array(nb_ped),
+                nb_rob=np.array(nb_rob), edge_mask=np.array(emask), p0=np.array(p0))
+
+
+def _lstm_last(w, mod, seq):
+    """nn.LSTM(batch_first) over [A,Th,in] from zero state, last output (model_utils.py:77-105 with full histories)."""
+    wih, whh = w[f"{mod}/weight_ih_l0"], w[f"{mod}/weight_hh_l0"]
+    b = w[f"{mod}/bias_ih_l0"] + w[f"{mod}/bias_hh_l0"]
+    A = seq.shape[0]
+    h = torch.zeros(A, 128); c = torch.zeros(A, 128)
+    for t in range(seq.shape[1]):
+        g = seq[:, t] @ wih.T + h @ whh.T + b
+        i, f, gg, o = g[:, :128], g[:, 128:256], g[:, 256:384], g[:, 384:]
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * torch.tanh(c)
+    return h
+
+
+def encode(w, inp):
+    """MultimodalGenerativeCVAE.obtain_encoded_tensors in PREDICT mode (mgcvae.py:505-681): ctx [A,256] fp32."""
+    x_st = torch.tensor(inp["x_st"], dtype=torch.float32)
+    hist = _lstm_last(w, "PEDESTRIAN/node_history_encoder", x_st)
+    m = torch.tensor(inp["edge_mask"], dtype=torch.float32).view(-1, 1)
+    edges = []
+    for mod, key in (("PEDESTRIAN->PEDESTRIAN/edge_encoder", "nb_ped"), ("PEDESTRIAN->JRDB_ROBOT/edge_encoder", "nb_rob")):
+        joint = torch.cat([torch.tensor(inp[key], dtype=torch.float32), x_st], dim=-1)
+        edges.append(_lstm_last(w, mod, joint) * m)
+    a = "PEDESTRIAN/edge_influence_encoder/"
+    scores = torch.cat([torch.tanh(e @ w[a + "w1.weight"].T + hist @ w[a + "w2.weight"].T) @ w[a + "v.weight"].T for e in edges], dim=1)
+    p = torch.softmax(scores, dim=1)
+    combined = p[:, 0:1] * edges[0] + p[:, 1:2] * edges[1]
+    return torch.cat([combined, hist], dim=1)
+
+
+def most_likely_samples(forecasts, k):
+    """get_most_likely_samples, joint branch (mid_sim_wrapper.py:14-169; quirk q4: always joint).
+    forecasts [S,A,T,2] torch -> ([A,k,T,2], logw [A,k])."""
+    S, A, T, _ = forecasts.shape
+    preds = forecasts.permute(2, 0, 1, 3).reshape(T, S, A * 2)
+    bandwidth = torch.exp(torch.linspace(np.log(0.01), np.log(0.1), steps=T))
+    n, d = torch.tensor(float(S)), 2 * A
+    diff = preds - preds.mean(dim=1, keepdim=True)
+    cov = torch.bmm(diff.transpose(1, 2), diff) / (n - 1)
+    sci = bandwidth[:, None, None] ** -2 * cov + torch.eye(d).expand_as(cov) * 1e-6
+    L = torch.linalg.cholesky_ex(torch.inverse(sci))[0]
+    diffs = preds.unsqueeze(2) - preds.unsqueeze(1)
+    diffs = torch.matmul(diffs, torch.linalg.inv(L).unsqueeze(1)) / bandwidth[:, None, None, None]
+    log_exp = -0.5 * torch.norm(diffs, p=2, dim=-1) ** 2
+    log_det = 2 * torch.sum(torch.log(torch.diagonal(L, dim1=-2, dim2=-1)), dim=-1)
+    Z = 0.5 * d * torch.log(torch.tensor(2 * np.pi)) + 0.5 * log_det.unsqueeze(-1) + torch.log(n)
+    ll = torch.logsumexp(log_exp - Z.unsqueeze(-1), dim=-1)
+    ll = ll - torch.logsumexp(ll, dim=1, keepdim=True)
+    tot = ll.sum(0)
+    top = torch.argsort(tot)[-k:]
+    lw = tot[top] - torch.logsumexp(tot[top], dim=-1, keepdim=True)
+    return forecasts[top].permute(1, 0, 2, 3), lw.unsqueeze(0).expand(A, k)
+
+
+def predict_ret_best(enc_w, ddpm_w, hist, robot_hist, x_T, num_draw, num_ret, step, dt=0.25, horizon=8, joint=True):
+    """HumanTrajectoryForecasterSim.predict_ret_best (mid_sim_wrapper.py:482-509) with injected noise x_T [S*A,T,2].
+    Returns (forecasts [H,k,T+1,2] float64, logw [H,k] float64, ctx [A,256])."""
+    H = hist.shape[0]
+    inp = encoder_inputs(hist, robot_hist, dt)
+    ctx = encode(enc_w, inp)
+    vel = JO.sample(ddpm_w, ctx, x_T, step=step, joint=joint)                       # [S,A,T,2]
+    pos = JO.integrate(vel, torch.tensor(inp["p0"], dtype=torch.float32), dt)       # ascending human id == sort by node id
+    if num_ret < num_draw:
+        fc_in, lw_in = most_likely_samples(pos, num_ret)
+        fc_in, lw_in = fc_in.numpy(), lw_in.numpy()
+    else:
+        fc_in = pos.permute(1, 0, 2, 3).numpy()
+        lw_in = np.log(np.ones((pos.shape[1], num_draw), np.float64) / num_draw)
+    forecasts = np.zeros((H, num_ret, horizon, 2), np.float64)
+    logw = np.zeros((H, num_ret), np.float64)
+    forecasts[inp["ped_ids"]] = fc_in
+    logw[inp["ped_ids"]] = lw_in
+    for h in range(H):
+        if inp["in_cluster"][h]:
+            continue
+        st = node_states(hist[h, :, :2], dt)                                         # constant-velocity fall-back (:413-429)
+        fc = np.zeros((horizon, 2))
+        fc[:, 0] = st[-1, 0] + np.cumsum(np.tile(st[-1, 2] * dt, horizon))
+        fc[:, 1] = st[-1, 1] + np.cumsum(np.tile(st[-1, 3] * dt, horizon))
+        forecasts[h] = fc[None]
+        logw[h] = lw_in[0]
+    cur = np.repeat(hist[:, -1, None, None, :2], num_ret, axis=1)                  # add_current_pose_to_forecasts (:444-454)
+    return np.concatenate([cur, forecasts], axis=2), logw, ctx
+
+
+def mpc_ingest(forecasts, logw, dt=0.25, horiz=4, joint=True):
+    """SICNavAcados.predict ingest (sicnav_acados.py:1645-1667): returns (forecasts_reshaped [horiz+1, H*k, 2], weights,
+    goals [H,2], v_pref [H])."""
+    fc = forecasts[:, :, 1:, :]
+    weights = logw[0, :] if joint else logw
+    H, k, T, _ = fc.shape
+    resh = np.transpose(fc, (2, 0, 1, 3)).reshape(T, H * k, 2)[:horiz + 1]
+    goals = fc[:, :, 0, :].mean(axis=1)
+    v = np.linalg.norm(np.diff(forecasts, axis=2), axis=-1) / dt
+    return resh, weights, goals, v.max(axis=(1, 2))

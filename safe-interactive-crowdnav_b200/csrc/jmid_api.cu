@@ -38,7 +38,8 @@ struct SnbJmid {
     float betas[101], alpha_bars[101];
     // activations for one chunk
     bf16 *h, *y, *qkv, *att, *ff, *t3, *t4;
-    float *pre, *xa, *xb, *gc, *bc, *gate, *hb;
+    bf16 *pre;
+    float *xa, *xb, *gc, *bc, *gate, *hb;
     std::map<int, Plans> plans;
     // CUDA graphs of one chunk's whole DDIM loop, keyed by (envs in chunk, n_steps); captured on second use
     float *ctx_stage = nullptr;
@@ -90,9 +91,9 @@ int get_plans(SnbJmid *h, int n_env, Plans **out)
     int rc = 0;
     for (int l = 0; l < NL && !rc; ++l) {
         rc = snb_gemm_plan(&p.qkv[l], h->h, h->L[l].wqkv, h->qkv, 0, p.M, 3 * D, D);
-        if (!rc) rc = snb_gemm_plan(&p.out[l], h->att, h->L[l].wo, h->pre, 1, p.M, D, D);
+        if (!rc) rc = snb_gemm_plan(&p.out[l], h->att, h->L[l].wo, h->pre, 0, p.M, D, D);
         if (!rc) rc = snb_gemm_plan(&p.ff1[l], h->y, h->L[l].w1, h->ff, 0, p.M, DFF, D);
-        if (!rc) rc = snb_gemm_plan(&p.ff2[l], h->ff, h->L[l].w2, h->pre, 1, p.M, D, DFF);
+        if (!rc) rc = snb_gemm_plan(&p.ff2[l], h->ff, h->L[l].w2, h->pre, 0, p.M, D, DFF);
     }
     if (!rc) rc = snb_gemm_plan(&p.c3, h->h, h->wc3, h->t3, 0, p.M, 256, D);
     if (!rc) rc = snb_gemm_plan(&p.c4, h->t3, h->wc4, h->t4, 0, p.M, 128, 256);
@@ -120,12 +121,12 @@ int net_forward(SnbJmid *h, Plans *P, const float *x_in, float *x_next, float *e
         else rc = snb_attn_small_launch(h->qkv, h->att, M / h->T, h->T, s);
         if (rc) return rc;
         e.bias = h->L[l].bo;
-        if ((rc = snb_gemm_launch(&P->out[l], EPI_BIAS_F32, &e, h->num_sms, s))) return rc;
+        if ((rc = snb_gemm_launch(&P->out[l], EPI_BIAS_BF16, &e, h->num_sms, s))) return rc;
         if ((rc = snb_k_layernorm(h->pre, h->h, h->L[l].n1w, h->L[l].n1b, h->y, M, s))) return rc;   // y = LN1(h + attn)
         e.bias = h->L[l].b1;
         if ((rc = snb_gemm_launch(&P->ff1[l], EPI_BIAS_RELU_BF16, &e, h->num_sms, s))) return rc;
         e.bias = h->L[l].b2;
-        if ((rc = snb_gemm_launch(&P->ff2[l], EPI_BIAS_F32, &e, h->num_sms, s))) return rc;
+        if ((rc = snb_gemm_launch(&P->ff2[l], EPI_BIAS_BF16, &e, h->num_sms, s))) return rc;
         if ((rc = snb_k_layernorm(h->pre, h->y, h->L[l].n2w, h->L[l].n2b, h->h, M, s))) return rc;   // h = LN2(y + ff)
     }
     memset(&e, 0, sizeof(e));
@@ -163,7 +164,7 @@ extern "C" int snb_jmid_create(SnbJmid **out, const SnbJmidWeights *w, int32_t m
     h->A = A; h->S = S; h->T = T; h->joint = joint ? 1 : 0; h->max_envs = max_envs; h->N = A * S * T;
     SNB_CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev));
     const char *ce = getenv("SNB_JMID_CHUNK");
-    int chunk = ce ? atoi(ce) : 16;
+    int chunk = ce ? atoi(ce) : 128;
     if (chunk < 1) chunk = 1;
     h->chunk_envs = chunk < max_envs ? chunk : max_envs;
     int rc = 0;

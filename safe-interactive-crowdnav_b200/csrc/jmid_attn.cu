@@ -154,24 +154,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
             __syncwarp();                 // reconverge before the .sync.aligned TMEM loads
             tc::tc_fence_after();
             const uint32_t s_addr = tmem_base + lane_addr + (st ? TM_S1 : TM_S0);
-            float s[BKV];
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                uint32_t r[32];
-                tc::tmem_ld_32x32(s_addr + ch * 32, r);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) s[ch * 32 + i] = __uint_as_float(r[i]);
-            }
+            // the whole S row: four 32-column loads in flight, ONE tcgen05.wait::ld
+            uint32_t s0[32], s1[32], s2[32], s3[32];
+            tc::tmem_ld_32x32(s_addr, s0);
+            tc::tmem_ld_32x32(s_addr + 32, s1);
+            tc::tmem_ld_32x32(s_addr + 64, s2);
+            tc::tmem_ld_32x32(s_addr + 96, s3);
+            tc::tmem_ld_wait();
             const int valid = n_tok - j * BKV; // keys of this block that exist
-            float bmax = -INFINITY;
-            if (valid >= BKV) {
+            if (valid < BKV) {                 // ragged last block: keys that do not exist score -inf
 #pragma unroll
-                for (int i = 0; i < BKV; ++i) bmax = fmaxf(bmax, s[i]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < BKV; ++i) { if (i >= valid) s[i] = -INFINITY; bmax = fmaxf(bmax, s[i]); }
+                for (int i = 0; i < 32; ++i) {
+                    if (i >= valid) s0[i] = 0xff800000u;
+                    if (32 + i >= valid) s1[i] = 0xff800000u;
+                    if (64 + i >= valid) s2[i] = 0xff800000u;
+                    if (96 + i >= valid) s3[i] = 0xff800000u;
+                }
             }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                mx0 = fmaxf(mx0, __uint_as_float(s0[i])); mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
+                mx2 = fmaxf(mx2, __uint_as_float(s2[i])); mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
+            }
+            const float bmax = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
             if (j == 0) {
                 m_used = bmax;
             } else if (__any_sync(0xffffffffu, (bmax - m_used) * c > RESCALE_THRESHOLD)) {
@@ -197,20 +203,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
                 m_used = m_new;
             }
             const float mc = m_used * c;
-            float sum = 0.0f;
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
+            float sum0 = 0.0f, sum1 = 0.0f, sum2 = 0.0f, sum3 = 0.0f;
+            {
                 uint32_t pk[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float p0 = tc::ex2_approx(fmaf(s[ch * 64 + 2 * i], c, -mc));
-                    const float p1 = tc::ex2_approx(fmaf(s[ch * 64 + 2 * i + 1], c, -mc));
-                    sum += p0 + p1;
-                    pk[i] = tc::pack_bf16(p0, p1);
+                for (int i = 0; i < 16; ++i) {
+                    const float a0 = tc::ex2_approx(fmaf(__uint_as_float(s0[2 * i]), c, -mc)), a1 = tc::ex2_approx(fmaf(__uint_as_float(s0[2 * i + 1]), c, -mc));
+                    const float b0 = tc::ex2_approx(fmaf(__uint_as_float(s1[2 * i]), c, -mc)), b1 = tc::ex2_approx(fmaf(__uint_as_float(s1[2 * i + 1]), c, -mc));
+                    sum0 += a0; sum1 += a1; sum2 += b0; sum3 += b1;
+                    pk[i] = tc::pack_bf16(a0, a1); pk[16 + i] = tc::pack_bf16(b0, b1);
                 }
-                tc::tmem_st_32x32(s_addr + ch * 32, pk); // P (bf16 pairs) overwrites the first 64 columns of S
+                tc::tmem_st_32x32(s_addr, pk);          // P columns [0,32)  <- S columns [0,64)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float a0 = tc::ex2_approx(fmaf(__uint_as_float(s2[2 * i]), c, -mc)), a1 = tc::ex2_approx(fmaf(__uint_as_float(s2[2 * i + 1]), c, -mc));
+                    const float b0 = tc::ex2_approx(fmaf(__uint_as_float(s3[2 * i]), c, -mc)), b1 = tc::ex2_approx(fmaf(__uint_as_float(s3[2 * i + 1]), c, -mc));
+                    sum0 += a0; sum1 += a1; sum2 += b0; sum3 += b1;
+                    pk[i] = tc::pack_bf16(a0, a1); pk[16 + i] = tc::pack_bf16(b0, b1);
+                }
+                tc::tmem_st_32x32(s_addr + 32, pk);     // P columns [32,64) <- S columns [64,128)
             }
-            l += sum;
+            l += (sum0 + sum1) + (sum2 + sum3);
             tc::tmem_st_wait();
             tc::tc_fence_before();
             tc::mbar_arrive(&p_ready[st]);

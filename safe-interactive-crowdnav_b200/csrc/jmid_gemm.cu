@@ -12,6 +12,7 @@
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of
 // tile i+1; CTAs are persistent (grid = #SMs) and walk the tile list with N fastest so that concurrently running
 // CTAs share the same A rows in L2.
+#include <cstdlib>
 #include <mutex>
 
 #include "jmid_internal.h"
@@ -21,7 +22,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
+constexpr int EPI_WARPS = 8;
 constexpr int STAGING_BYTES = 32 * 128; // per epilogue warp: 32 rows x 128 B (one swizzle atom wide)
 
 template <int BN> struct GemmCfg {
@@ -31,7 +33,7 @@ template <int BN> struct GemmCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BN; // 512 or 256: both powers of two
     static constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
-    static constexpr int OFF_BIAS = OFF_STAGING + 4 * STAGING_BYTES;
+    static constexpr int OFF_BIAS = OFF_STAGING + EPI_WARPS * STAGING_BYTES;
     static constexpr int OFF_BARS = OFF_BIAS + BN * 4;
     static constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024 /*align*/;
 };
@@ -71,13 +73,64 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&acc)[32], float (
 // 16-byte chunk `c` (0..7) of row `r` (0..31) inside a 32 x 128 B staging tile with the TMA 128-byte swizzle
 __device__ __forceinline__ uint4 *staging_slot(uint8_t *stg, int r, int c) { return reinterpret_cast<uint4 *>(stg + r * 128 + ((c ^ (r & 7)) << 4)); }
 
+// Drains columns [c_begin, c_end) (multiples of 64) of one warp's 32 accumulator rows: software-pipelined tcgen05.ld ->
+// bias / ReLU / ConcatSquash -> 128B-swizzled staging tile -> one TMA store per 128 bytes of output row.
+template <int EPI>
+__device__ __forceinline__ void epilogue_drain(uint32_t t_addr, uint8_t *stg, const float *s_bias, const GemmEpi &ep,
+                                               const CUtensorMap *tmC, int n0, int row0, int ba, int c_begin, int c_end, int lane)
+{
+    constexpr bool OUT_F32 = (EPI == EPI_BIAS_F32);
+    uint32_t ra[32], rb[32];
+    float v[32];
+    tc::tmem_ld_32x32(t_addr + c_begin, ra);
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 64) {
+        tc::tmem_ld_wait();
+        tc::tmem_ld_32x32(t_addr + c + 32, rb);
+        epilogue_math<EPI>(ra, v, s_bias + c, ep, n0 + c, ba);
+        if (lane == 0) tc::tma_store_wait_read<0>();
+        __syncwarp();
+        if constexpr (OUT_F32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *staging_slot(stg, lane, j) = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { tc::tma_store_2d(tmC, stg, n0 + c, row0); tc::tma_store_commit(); }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *staging_slot(stg, lane, j) = make_uint4(tc::pack_bf16(v[8 * j], v[8 * j + 1]), tc::pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                                         tc::pack_bf16(v[8 * j + 4], v[8 * j + 5]), tc::pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+        }
+        tc::tmem_ld_wait();
+        if (c + 64 < c_end) tc::tmem_ld_32x32(t_addr + c + 64, ra);
+        epilogue_math<EPI>(rb, v, s_bias + c + 32, ep, n0 + c + 32, ba);
+        if constexpr (OUT_F32) {
+            if (lane == 0) tc::tma_store_wait_read<0>();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *staging_slot(stg, lane, j) = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { tc::tma_store_2d(tmC, stg, n0 + c + 32, row0); tc::tma_store_commit(); }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *staging_slot(stg, lane, 4 + j) = make_uint4(tc::pack_bf16(v[8 * j], v[8 * j + 1]), tc::pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                                             tc::pack_bf16(v[8 * j + 4], v[8 * j + 5]), tc::pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { tc::tma_store_2d(tmC, stg, n0 + c, row0); tc::tma_store_commit(); }
+        }
+    }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const GemmEpi ep, const int M, const int N, const int K)
 {
     using Cfg = GemmCfg<BN>;
-    constexpr bool OUT_F32 = (EPI == EPI_BIAS_F32);
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::OFF_BARS);
@@ -95,7 +148,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc::prefetch_tmap(&tmB);
         tc::prefetch_tmap(&tmC);
         for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { tc::mbar_init(&tfull[s], 1); tc::mbar_init(&tempty[s], 128); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&tfull[s], 1); tc::mbar_init(&tempty[s], EPI_WARPS); }
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -152,10 +205,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int quarter = warp & 3; // TMEM lanes [32*quarter, 32*quarter + 32)
+        // ===================== epilogue (warps 2..9) =====================
+        const int quarter = warp & 3;            // TMEM lanes [32*quarter, 32*quarter + 32)
+        const int half = (warp - 2) >> 2;        // which half of the tile's BN columns this warp drains
         const int etid = (warp - 2) * 32 + lane;
-        uint8_t *stg = smem + Cfg::OFF_STAGING + quarter * STAGING_BYTES;
+        uint8_t *stg = smem + Cfg::OFF_STAGING + (warp - 2) * STAGING_BYTES;
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -171,75 +225,172 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 ba = b * ep.A + (r % ep.A);
             }
             // this tile's bias slice -> smem (the previous tile's readers are past their last use: barrier below)
-            tc::named_bar_sync(1, 128);
-            for (int i = etid; i < BN; i += 128) s_bias[i] = __ldg(ep.bias + n0 + i);
-            tc::named_bar_sync(1, 128);
+            tc::named_bar_sync(1, EPI_WARPS * 32);
+            for (int i = etid; i < BN; i += EPI_WARPS * 32) s_bias[i] = __ldg(ep.bias + n0 + i);
+            tc::named_bar_sync(1, EPI_WARPS * 32);
 
             tc::mbar_wait(&tfull[acc], acc_phase);
             __syncwarp();                 // reconverge before the .sync.aligned TMEM loads
             tc::tc_fence_after();
             const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
-            uint32_t ra[32], rb[32];
-            float v[32];
-            tc::tmem_ld_32x32(t_addr, ra);
-            if constexpr (OUT_F32) {
-                // fp32 output: one 32-column chunk = 128 B per row = one store unit
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; c += 2) {
-                    tc::tmem_ld_wait();
-                    tc::tmem_ld_32x32(t_addr + (c + 1) * 32, rb);
-                    epilogue_math<EPI>(ra, v, s_bias + c * 32, ep, n0 + c * 32, ba);
-                    if (lane == 0) tc::tma_store_wait_read<0>();
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) *staging_slot(stg, lane, j) = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
-                    tc::fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) { tc::tma_store_2d(&tmC, stg, n0 + c * 32, row0); tc::tma_store_commit(); }
-                    tc::tmem_ld_wait();
-                    if (c + 2 < BN / 32) tc::tmem_ld_32x32(t_addr + (c + 2) * 32, ra);
-                    epilogue_math<EPI>(rb, v, s_bias + (c + 1) * 32, ep, n0 + (c + 1) * 32, ba);
-                    if (lane == 0) tc::tma_store_wait_read<0>();
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) *staging_slot(stg, lane, j) = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
-                    tc::fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) { tc::tma_store_2d(&tmC, stg, n0 + (c + 1) * 32, row0); tc::tma_store_commit(); }
-                }
-            } else {
-                // bf16 output: two 32-column chunks = 128 B per row = one store unit
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; c += 2) {
-                    tc::tmem_ld_wait();
-                    tc::tmem_ld_32x32(t_addr + (c + 1) * 32, rb);
-                    epilogue_math<EPI>(ra, v, s_bias + c * 32, ep, n0 + c * 32, ba);
-                    if (lane == 0) tc::tma_store_wait_read<0>();
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        *staging_slot(stg, lane, j) = make_uint4(tc::pack_bf16(v[8 * j], v[8 * j + 1]), tc::pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                                                 tc::pack_bf16(v[8 * j + 4], v[8 * j + 5]), tc::pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-                    tc::tmem_ld_wait();
-                    if (c + 2 < BN / 32) tc::tmem_ld_32x32(t_addr + (c + 2) * 32, ra);
-                    epilogue_math<EPI>(rb, v, s_bias + (c + 1) * 32, ep, n0 + (c + 1) * 32, ba);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        *staging_slot(stg, lane, 4 + j) = make_uint4(tc::pack_bf16(v[8 * j], v[8 * j + 1]), tc::pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                                                     tc::pack_bf16(v[8 * j + 4], v[8 * j + 5]), tc::pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-                    tc::fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) { tc::tma_store_2d(&tmC, stg, n0 + c * 32, row0); tc::tma_store_commit(); }
-                }
-            }
-            // every TMEM load of this tile has completed (last tmem_ld_wait above): hand the accumulator back
+            epilogue_drain<EPI>(t_addr, stg, s_bias, ep, &tmC, n0, row0, ba, half * (BN / 2), (half + 1) * (BN / 2), lane);
+            // every TMEM load of this warp has completed (last tmem_ld_wait inside): hand the accumulator back
             tc::tc_fence_before();
-            tc::mbar_arrive(&tempty[acc]);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tempty[acc]);
         }
         if (lane == 0) tc::tma_store_wait<0>();
     }
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN tile.  Each CTA stages its
+// own 128 rows of A and HALF of the W tile (BN/2 rows); one MMA issued by the pair's leader reads both CTAs' shared memory
+// and writes each CTA's 128 accumulator rows into its own TMEM.  Per CTA and k-block this moves 32 KB instead of 48 KB
+// through L2 / the shared-memory ports for the same number of MACs, which is what lifts the 1-CTA kernel's ~66 % ceiling
+// (UMMA operand reads + TMA fills exceed 128 B/clk/SM there).
+template <int BN> struct Gemm2Cfg {
+    static constexpr int STAGES = 6;
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = (BN / 2) * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
+    static constexpr int OFF_BIAS = OFF_STAGING + EPI_WARPS * STAGING_BYTES;
+    static constexpr int OFF_BARS = OFF_BIAS + BN * 4;
+    static constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;
+};
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmC, const GemmEpi ep, const int M, const int N, const int K)
+{
+    using Cfg = Gemm2Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::OFF_BARS);
+    uint64_t *full = bars, *empty = bars + Cfg::STAGES, *tfull = bars + 2 * Cfg::STAGES, *tempty = bars + 2 * Cfg::STAGES + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * Cfg::STAGES + 4);
+    float *s_bias = reinterpret_cast<float *>(smem + Cfg::OFF_BIAS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int m_tiles = (M + 2 * BM - 1) / (2 * BM), n_tiles = N / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int k_blocks = K / BK;
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmA); tc::prefetch_tmap(&tmB); tc::prefetch_tmap(&tmC);
+        for (int s = 0; s < Cfg::STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }   // full: armed by the leader for both CTAs' bytes
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&tfull[s], 1); tc::mbar_init(&tempty[s], 2 * EPI_WARPS); }  // tempty: both epilogues
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();          // the peer's barriers are initialised before anything arrives on them
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one per CTA) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = pair; t < num_tiles; t += n_pairs) {
+                const int m0 = (t / n_tiles) * (2 * BM) + (int)rank * BM, n0 = (t % n_tiles) * BN + (int)rank * (BN / 2);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    tc::mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t *a = smem + stage * Cfg::STAGE_BYTES;
+                    // the leader arms its barrier with the bytes of BOTH CTAs; the peer's loads complete_tx on the same barrier
+                    // (its stage cannot be refilled before the leader's previous phase finished: empty[] is signalled by
+                    // the commit that follows the MMAs which waited on that phase)
+                    if (leader) tc::mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+                    tc::tma_load_2d_pair(a, &tmA, &full[stage], kb * BK, m0);
+                    tc::tma_load_2d_pair(a + Cfg::A_BYTES, &tmB, &full[stage], kb * BK, n0);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = tc::make_idesc_bf16(2 * BM, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = pair; t < num_tiles; t += n_pairs, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    tc::mbar_wait(&full[stage], phase);
+                    tc::tc_fence_after();
+                    const uint32_t a_addr = tc::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t da = tc::make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+                        const uint64_t db = tc::make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                        tc::umma_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    tc::umma_commit_pair(&empty[stage]);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc::umma_commit_pair(&tfull[acc]);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..9 of both CTAs; each CTA drains its own 128 accumulator rows) ==========
+        const int quarter = warp & 3;            // TMEM lanes [32*quarter, 32*quarter + 32)
+        const int half = (warp - 2) >> 2;        // which half of the tile's BN columns this warp drains
+        const int etid = (warp - 2) * 32 + lane;
+        uint8_t *stg = smem + Cfg::OFF_STAGING + (warp - 2) * STAGING_BYTES;
+        int it = 0;
+        for (int t = pair; t < num_tiles; t += n_pairs, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int m0 = (t / n_tiles) * (2 * BM) + (int)rank * BM, n0 = (t % n_tiles) * BN;
+            const int row0 = m0 + quarter * 32;
+            int ba = 0;
+            if constexpr (EPI == EPI_CSL_BF16) {
+                int row = row0 + lane;
+                if (row >= M) row = M - 1;
+                const int b = row / ep.tok_per_env;
+                const int r = (row - b * ep.tok_per_env) / ep.T;
+                ba = b * ep.A + (r % ep.A);
+            }
+            // this tile's bias slice -> smem (the previous tile's readers are past their last use: barrier below)
+            tc::named_bar_sync(1, EPI_WARPS * 32);
+            for (int i = etid; i < BN; i += EPI_WARPS * 32) s_bias[i] = __ldg(ep.bias + n0 + i);
+            tc::named_bar_sync(1, EPI_WARPS * 32);
+
+            tc::mbar_wait(&tfull[acc], acc_phase);
+            __syncwarp();                 // reconverge before the .sync.aligned TMEM loads
+            tc::tc_fence_after();
+            const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
+            epilogue_drain<EPI>(t_addr, stg, s_bias, ep, &tmC, n0, row0, ba, half * (BN / 2), (half + 1) * (BN / 2), lane);
+            // every TMEM load of this warp has completed (last tmem_ld_wait inside): hand the accumulator back
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (leader) tc::mbar_arrive(&tempty[acc]);
+                else tc::mbar_arrive_cluster(tc::mapa_u32(&tempty[acc], 0));
+            }
+        }
+        if (lane == 0) tc::tma_store_wait<0>();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();          // nobody leaves while the pair's MMAs / commits may still touch its shared memory
+    if (warp == 1) tc::tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -279,9 +430,41 @@ int launch_t(const GemmPlan *p, const GemmEpi *ep, int num_sms, cudaStream_t str
     return SNB_OK;
 }
 
+template <int BN, int EPI>
+int launch2_t(const GemmPlan *p, const GemmEpi *ep, int num_sms, cudaStream_t stream)
+{
+    using Cfg = Gemm2Cfg<BN>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    });
+    SNB_CUDA_TRY(attr_err);
+    const int tiles = ((p->M + 2 * BM - 1) / (2 * BM)) * (p->N / BN);
+    const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
+    gemm2_bf16_tn_kernel<BN, EPI><<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p->tmA, p->tmB2, p->tmC, *ep, p->M, p->N, p->K);
+    snb_count_launch();
+    SNB_CUDA_TRY(cudaGetLastError());
+    return SNB_OK;
+}
+
+bool use_pair_kernel()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("SNB_GEMM_2CTA"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+
 template <int BN>
 int launch_bn(const GemmPlan *p, int kind, const GemmEpi *ep, int num_sms, cudaStream_t stream)
 {
+    if (BN == 256 && use_pair_kernel() && kind != EPI_BIAS_F32) {
+        switch (kind) {
+        case EPI_BIAS_BF16: return launch2_t<256, EPI_BIAS_BF16>(p, ep, num_sms, stream);
+        case EPI_BIAS_RELU_BF16: return launch2_t<256, EPI_BIAS_RELU_BF16>(p, ep, num_sms, stream);
+        case EPI_CSL_BF16: return launch2_t<256, EPI_CSL_BF16>(p, ep, num_sms, stream);
+        }
+    }
     switch (kind) {
     case EPI_BIAS_BF16: return launch_t<BN, EPI_BIAS_BF16>(p, ep, num_sms, stream);
     case EPI_BIAS_RELU_BF16: return launch_t<BN, EPI_BIAS_RELU_BF16>(p, ep, num_sms, stream);
@@ -330,6 +513,8 @@ int snb_gemm_plan(GemmPlan *plan, const bf16 *A, const bf16 *W, void *out, int o
     int rc = snb_make_tmap_2d(&plan->tmA, A, (uint64_t)M, (uint64_t)K, BM);
     if (rc) return rc;
     rc = snb_make_tmap_2d(&plan->tmB, W, (uint64_t)N, (uint64_t)K, (uint32_t)plan->BN);
+    if (rc) return rc;
+    rc = snb_make_tmap_2d(&plan->tmB2, W, (uint64_t)N, (uint64_t)K, (uint32_t)plan->BN / 2);   // CTA-pair kernel: half of W per CTA
     if (rc) return rc;
     // output [M, N]: store unit = 32 rows x 128 bytes
     const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};

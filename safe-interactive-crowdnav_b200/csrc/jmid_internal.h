@@ -32,7 +32,7 @@ struct GemmEpi {
 };
 
 struct GemmPlan {
-    CUtensorMap tmA, tmB, tmC; // tmC: output [M,N] (bf16 or fp32), written with TMA stores of 32 rows x 128 B
+    CUtensorMap tmA, tmB, tmB2, tmC; // tmB2: W with box BN/2 rows (CTA-pair kernel); tmC: output [M,N] (bf16 or fp32), written with TMA stores of 32 rows x 128 B
     int M, N, K, BN, out_f32;
 };
 int snb_gemm_plan(GemmPlan *plan, const bf16 *A, const bf16 *W, void *out, int out_f32, int M, int N, int K);
@@ -60,8 +60,8 @@ int snb_k_hyper_iter(const HyperW *layers4, const float *gc, const float *bc, fl
 // concat1 + positional encoding: h[m, 512] = (W1 x[m] + b1) * gate[ba, 0:512] + hb[ba, 0:512] + pe[tau]
 int snb_k_embed(const float *x, const float *w1, const float *b1, const float *gate, const float *hb, const float *pe, bf16 *h,
                 int n_tok_total, int tok_per_env, int T, int A, cudaStream_t s);
-// out_bf16 = LayerNorm(512)(in_f32 + resid_bf16)
-int snb_k_layernorm(const float *in, const bf16 *resid, const float *g, const float *b, bf16 *out, int rows, cudaStream_t s);
+// out_bf16 = LayerNorm(512)(in_bf16 + resid_bf16), fp32 statistics
+int snb_k_layernorm(const bf16 *in, const bf16 *resid, const float *g, const float *b, bf16 *out, int rows, cudaStream_t s);
 // final ConcatSquash 128 -> 2 and the DDIM update of x_t (diffusion.py:524-528); eps_out optional
 int snb_k_tail_ddim(const bf16 *t4, const float *wl, const float *bl, const float *gate, const float *hb, int tab_ld,
                     const float *x_t, float *x_next, float *eps_out, int n_tok_total, int tok_per_env, int T, int A,

@@ -79,47 +79,51 @@ __global__ void embed_kernel(const float *__restrict__ x, const float *__restric
     *reinterpret_cast<uint2 *>(h + (size_t)tok * 512 + c4) = o;
 }
 
-// LayerNorm over 512 fp32 columns, one warp per row (eps 1e-5, biased variance like torch)
-__global__ void layernorm_kernel(const float *__restrict__ in, const bf16 *__restrict__ resid, const float *__restrict__ g,
+// out = LayerNorm(pre + resid) over 512 columns, one warp per row (eps 1e-5, biased variance like torch); `pre` (the
+// sub-layer output written by the GEMM epilogue) and `resid` are bf16, statistics and normalisation are fp32
+__global__ void layernorm_kernel(const bf16 *__restrict__ pre, const bf16 *__restrict__ resid, const float *__restrict__ g,
                                  const float *__restrict__ b, bf16 *__restrict__ out, int rows)
 {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    const float4 *p = reinterpret_cast<const float4 *>(in + (size_t)row * 512);
-    float4 v[4];
+    const uint4 *pp = reinterpret_cast<const uint4 *>(pre + (size_t)row * 512);
+    const uint4 *rp = reinterpret_cast<const uint4 *>(resid + (size_t)row * 512);
+    float v[16];
     float sum = 0.0f;
 #pragma unroll
-    const uint2 *rp = reinterpret_cast<const uint2 *>(resid + (size_t)row * 512);
+    for (int i = 0; i < 2; ++i) {
+        const uint4 a = pp[lane + 32 * i], r = rp[lane + 32 * i];
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        v[i] = p[lane + 32 * i];
-        const uint2 rr = rp[lane + 32 * i];
-        const __nv_bfloat162 r0 = *reinterpret_cast<const __nv_bfloat162 *>(&rr.x), r1 = *reinterpret_cast<const __nv_bfloat162 *>(&rr.y);
-        v[i].x += __bfloat162float(r0.x); v[i].y += __bfloat162float(r0.y); v[i].z += __bfloat162float(r1.x); v[i].w += __bfloat162float(r1.y);
-        sum += v[i].x + v[i].y + v[i].z + v[i].w;
+        for (int q = 0; q < 4; ++q) {
+            const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162 *>(&aw[q]), y = *reinterpret_cast<const __nv_bfloat162 *>(&rw[q]);
+            v[8 * i + 2 * q] = __bfloat162float(x.x) + __bfloat162float(y.x);
+            v[8 * i + 2 * q + 1] = __bfloat162float(x.y) + __bfloat162float(y.y);
+            sum += v[8 * i + 2 * q] + v[8 * i + 2 * q + 1];
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float mean = sum * (1.0f / 512.0f);
     float sq = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float a = v[i].x - mean, c = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
-        sq += a * a + c * c + d * d + e * e;
-    }
+    for (int i = 0; i < 16; ++i) { const float d = v[i] - mean; sq += d * d; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     const float rstd = rsqrtf(sq * (1.0f / 512.0f) + 1e-5f);
-    const float4 *g4 = reinterpret_cast<const float4 *>(g), *b4 = reinterpret_cast<const float4 *>(b);
-    uint2 *o2 = reinterpret_cast<uint2 *>(out + (size_t)row * 512);
+    uint4 *op = reinterpret_cast<uint4 *>(out + (size_t)row * 512);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float4 gg = __ldg(g4 + lane + 32 * i), bb = __ldg(b4 + lane + 32 * i);
-        uint2 o;
-        o.x = tc::pack_bf16((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y);
-        o.y = tc::pack_bf16((v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
-        o2[lane + 32 * i] = o;
+    for (int i = 0; i < 2; ++i) {
+        const int c0 = (lane + 32 * i) * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4 *>(g + c0)), g1 = __ldg(reinterpret_cast<const float4 *>(g + c0 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(b + c0)), b1 = __ldg(reinterpret_cast<const float4 *>(b + c0 + 4));
+        uint4 o;
+        o.x = tc::pack_bf16((v[8 * i + 0] - mean) * rstd * g0.x + b0.x, (v[8 * i + 1] - mean) * rstd * g0.y + b0.y);
+        o.y = tc::pack_bf16((v[8 * i + 2] - mean) * rstd * g0.z + b0.z, (v[8 * i + 3] - mean) * rstd * g0.w + b0.w);
+        o.z = tc::pack_bf16((v[8 * i + 4] - mean) * rstd * g1.x + b1.x, (v[8 * i + 5] - mean) * rstd * g1.y + b1.y);
+        o.w = tc::pack_bf16((v[8 * i + 6] - mean) * rstd * g1.z + b1.z, (v[8 * i + 7] - mean) * rstd * g1.w + b1.w);
+        op[lane + 32 * i] = o;
     }
 }
 
@@ -230,7 +234,7 @@ int snb_k_embed(const float *x, const float *w1, const float *b1, const float *g
     return SNB_OK;
 }
 
-int snb_k_layernorm(const float *in, const bf16 *resid, const float *g, const float *b, bf16 *out, int rows, cudaStream_t s)
+int snb_k_layernorm(const bf16 *in, const bf16 *resid, const float *g, const float *b, bf16 *out, int rows, cudaStream_t s)
 {
     layernorm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(in, resid, g, b, out, rows);
     snb_count_launch();
