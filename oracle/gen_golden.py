@@ -449,6 +449,10 @@ def gen_predictor():
     with torch.no_grad():
         rng = np.random.default_rng(2024)
         f = build(5, 20, 20, 20)
+        md0 = f.mid_model.registrar.model_dict            # the shipped encoder weights (1 MB) so the ckpt cases pin encode()
+        for k in PO.make_random_encoder_weights(seed=9):
+            mod, pname = k.rsplit("/", 1)
+            out["ckpt_enc:" + k] = dict(md0[mod].named_parameters())[pname].detach().numpy().copy()
         run("ckpt_h5", f, 5, rng, 1.5, False)
         run("ckpt_h5_sparse", f, 5, rng, 4.0, False)
         run("rand_h5", f, 5, rng, 1.5, True)

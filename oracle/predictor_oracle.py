@@ -215,6 +215,6 @@ def mpc_ingest(forecasts, logw, dt=0.25, horiz=4, joint=True):
     weights = logw[0, :] if joint else logw
     H, k, T, _ = fc.shape
     resh = np.transpose(fc, (2, 0, 1, 3)).reshape(T, H * k, 2)[:horiz + 1]
-    goals = fc[:, :, 0, :].mean(axis=1)
-    v = np.linalg.norm(np.diff(forecasts, axis=2), axis=-1) / dt
+    goals = np.array([[np.mean(fc[h, :, 0, 0]), np.mean(fc[h, :, 0, 1])] for h in range(H)])    # per human, as the reference loops
+    v = np.linalg.norm(np.diff(fc, axis=2), axis=-1) / dt                           # on the forecasts WITHOUT the current pose (:1667)
     return resh, weights, goals, v.max(axis=(1, 2))
