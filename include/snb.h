@@ -186,6 +186,13 @@ int snb_jmid_destroy(SnbJmid *h);
  */
 int snb_jmid_denoise(SnbJmid *h, const float *ctx_dev, const float *x_T_dev, float *out_vel_dev, int32_t B,
                      int32_t n_steps, void *stream);
+/* agents per environment chosen per call: A <= the handle's A; ctx [B,A,256], x_T [B,S*A,T,2], out [B,S,A,T,2].
+ * (the predictor's attention cluster changes size from step to step, mid_sim_wrapper.py:322-355) */
+int snb_jmid_denoise_agents(SnbJmid *h, const float *ctx_dev, const float *x_T_dev, float *out_vel_dev, int32_t B, int32_t A,
+                            int32_t n_steps, void *stream);
+/* sizes the handle was created with */
+int snb_jmid_dims(const SnbJmid *h, int32_t *A, int32_t *S, int32_t *T, int32_t *joint);
+
 /* one noise-network forward at diffusion step t (parity of JointPredictionTransformerConcatLinear.forward) */
 int snb_jmid_eps(SnbJmid *h, const float *ctx_dev, const float *x_t_dev, float *eps_dev, int32_t B, int32_t t,
                  void *stream);
@@ -208,6 +215,80 @@ int snb_jmid_gemm_bf16(const void *A_dev, const void *W_dev, const float *bias_d
 int snb_jmid_attention(const void *qkv_dev, void *out_dev, int32_t n_env, int32_t n_tok, void *stream);
 /* algorithmic FLOPs of one denoise iteration for one environment */
 double snb_jmid_flops_per_iter(int32_t A, int32_t S, int32_t T, int32_t joint);
+
+/* ======================================================================================================
+ * JMID predictor around the denoiser: what HumanTrajectoryForecasterSim.predict_ret_best does per call
+ * (sicnav_diffusion/JMID/mid_sim_wrapper.py:172-509), batched over B environments of H humans.
+ * ====================================================================================================== */
+
+typedef struct SnbLstmWeights { /* torch nn.LSTM(input, 128), one layer: weight_ih_l0 [512,input], weight_hh_l0 [512,128], gates i,f,g,o */
+    const float *w_ih, *w_hh, *b_ih, *b_hh;
+} SnbLstmWeights;
+
+typedef struct SnbEncoderWeights { /* checkpoint["encoder"], SURVEY Appendix B */
+    SnbLstmWeights node_history; /* PEDESTRIAN/node_history_encoder              LSTM(6 -> 128)  */
+    SnbLstmWeights edge_ped;     /* PEDESTRIAN->PEDESTRIAN/edge_encoder          LSTM(12 -> 128) */
+    SnbLstmWeights edge_robot;   /* PEDESTRIAN->JRDB_ROBOT/edge_encoder          LSTM(12 -> 128) */
+    const float *att_w1, *att_w2, *att_v; /* PEDESTRIAN/edge_influence_encoder  w1 [128,128], w2 [128,128], v [1,128] */
+} SnbEncoderWeights;
+
+typedef struct SnbPredictor SnbPredictor;
+
+/* Device-resident predictor for up to max_envs environments of H humans (H <= 31, H <= the denoiser's A).
+ * `denoiser` is borrowed (not destroyed with the predictor).  Replaces HumanTrajectoryForecasterSim.__init__ /
+ * _init_MID (mid_sim_wrapper.py:207-241). */
+int snb_pred_create(SnbPredictor **out, const SnbEncoderWeights *w_dev, SnbJmid *denoiser, int32_t max_envs, int32_t H,
+                    void *stream);
+int snb_pred_destroy(SnbPredictor *p);
+
+/* update_state_hists (mid_sim_wrapper.py:185-204): appends one frame of positions to the 6-frame rings; the frames must be
+ * dt apart (the reference's resampling, :283-310, is then the identity).  human_p{x,y}_dev [B,H], robot_p{x,y}_dev [B].
+ * The first push after create / reset fills every frame of the ring. */
+int snb_pred_push_history(SnbPredictor *p, const double *human_px_dev, const double *human_py_dev, const double *robot_px_dev,
+                          const double *robot_py_dev, int32_t B, void *stream);
+int snb_pred_reset_history(SnbPredictor *p);
+/* overwrite the rings: hist_dev [B,H,6,2], robot_hist_dev [B,6,2] (oldest frame first) */
+int snb_pred_set_history(SnbPredictor *p, const double *hist_dev, const double *robot_hist_dev, int32_t B, void *stream);
+
+/* convert_to_mid_state_env + get_timesteps_data + Trajectron.get_latent (mid_sim_wrapper.py:313-437, preprocessing.py:428-694,
+ * mgcvae.py:505-880) on the rings.  Outputs (each optional): ctx_dev [B,H,256] (slot a < n_in[b] = a-th in-cluster human in
+ * ascending id), n_in_dev [B], ped_ids_dev [B,H] (slot -> human, -1 unused), in_cluster_dev [B,H]. */
+int snb_pred_encode(SnbPredictor *p, int32_t B, double radius, double dt, float *ctx_dev, int32_t *n_in_dev,
+                    int32_t *ped_ids_dev, uint8_t *in_cluster_dev, void *stream);
+
+/* standard-normal noise (Philox4x32-10 + Box-Muller), element i a function of (seed, offset, i) only */
+int snb_pred_noise(float *out_dev, int64_t n, uint64_t seed, uint64_t offset, void *stream);
+
+/*
+ * predict_ret_best (mid_sim_wrapper.py:482-509) for B environments:
+ *   noise_dev [B,S,H,T,2] fp32 or NULL (then drawn from (seed, call counter)); environment b with A_b in-cluster humans uses
+ *   noise[b, s, a < A_b] as row s*A_b + a of the reference's x_T.
+ *   num_ret <= S samples are returned; num_ret < S selects them with the KDE top-k (get_most_likely_samples, :14-169).
+ *   forecasts_dev [B,H,num_ret,T+1,2] fp64 (frame 0 = current pose, constant-velocity rows outside the cluster),
+ *   logw_dev [B,H,num_ret] fp64.
+ * Environments are grouped by A_b and each group is denoised as one batch (one host synchronisation per call to read
+ * the B cluster sizes).
+ */
+int snb_pred_predict(SnbPredictor *p, int32_t B, const float *noise_dev, uint64_t seed, int32_t n_steps, int32_t num_ret,
+                     double radius, double dt, double *forecasts_dev, double *logw_dev, void *stream);
+/* host-buffer form (the plugin call): histories in, forecasts out, synchronous */
+int snb_pred_predict_host(SnbPredictor *p, const double *hist_host, const double *robot_hist_host, int32_t B,
+                          const float *noise_host, uint64_t seed, int32_t n_steps, int32_t num_ret, double radius, double dt,
+                          double *forecasts_host, double *logw_host);
+
+/* Component-level entry of the KDE top-k (get_most_likely_samples, mid_sim_wrapper.py:14-169; always the joint branch, quirk q4):
+ * pos_dev [B,S,A,T,2] fp32 -> sel_dev [B,k] sample indices in ascending total log-likelihood (ties: ascending index),
+ * logw_dev [B,k] fp64 = log-softmax of the kept totals. */
+int snb_pred_kde_topk(const float *pos_dev, int32_t B, int32_t S, int32_t A, int32_t T, int32_t k, int32_t *sel_dev,
+                      double *logw_dev, void *stream);
+
+/* MPC ingest (SICNavAcados.predict, sicnav_diffusion/policy/sicnav_acados.py:1645-1667):
+ *   resh_dev [B, min(T, horiz+1), H*k, 2]   'h s t d -> t (h s) d' of the forecasts without the current pose
+ *   weights_dev [B,k] (joint: logw[b,0,:]) or [B,H,k];  goals_dev [B,H,2] = mean over samples of the first predicted point;
+ *   vpref_dev [B,H] = max over samples and steps of |dp| / dt */
+int snb_pred_ingest(const double *forecasts_dev, const double *logw_dev, int32_t B, int32_t H, int32_t k, int32_t T,
+                    int32_t horiz, double dt, int32_t joint, double *resh_dev, double *weights_dev, double *goals_dev,
+                    double *vpref_dev, void *stream);
 
 #ifdef __cplusplus
 }

@@ -153,9 +153,11 @@ def encode(w, inp):
     return torch.cat([combined, hist], dim=1)
 
 
-def most_likely_samples(forecasts, k):
-    """get_most_likely_samples, joint branch (mid_sim_wrapper.py:14-169; quirk q4: always joint).
-    forecasts [S,A,T,2] torch -> ([A,k,T,2], logw [A,k])."""
+def kde_totals(forecasts):
+    """Per-sample total log-likelihood of get_most_likely_samples (mid_sim_wrapper.py:14-150), forecasts [S,A,T,2] -> [S].
+    NB with the shipped bandwidths (0.01 .. 0.1, applied on top of the covariance whitening) the kernel is so narrow that every
+    sample only sees itself unless two samples nearly coincide: all totals are then EXACTLY T*log(1/S) and the reference's
+    top-k is decided by the tie order of torch.argsort."""
     S, A, T, _ = forecasts.shape
     preds = forecasts.permute(2, 0, 1, 3).reshape(T, S, A * 2)
     bandwidth = torch.exp(torch.linspace(np.log(0.01), np.log(0.1), steps=T))
@@ -171,7 +173,14 @@ def most_likely_samples(forecasts, k):
     Z = 0.5 * d * torch.log(torch.tensor(2 * np.pi)) + 0.5 * log_det.unsqueeze(-1) + torch.log(n)
     ll = torch.logsumexp(log_exp - Z.unsqueeze(-1), dim=-1)
     ll = ll - torch.logsumexp(ll, dim=1, keepdim=True)
-    tot = ll.sum(0)
+    return ll.sum(0)
+
+
+def most_likely_samples(forecasts, k):
+    """get_most_likely_samples, joint branch (mid_sim_wrapper.py:14-169; quirk q4: always joint).
+    forecasts [S,A,T,2] torch -> ([A,k,T,2], logw [A,k])."""
+    S, A, T, _ = forecasts.shape
+    tot = kde_totals(forecasts)
     top = torch.argsort(tot)[-k:]
     lw = tot[top] - torch.logsumexp(tot[top], dim=-1, keepdim=True)
     return forecasts[top].permute(1, 0, 2, 3), lw.unsqueeze(0).expand(A, k)

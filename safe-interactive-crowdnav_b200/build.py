@@ -26,6 +26,10 @@ UNITS = [
     ("jmid_gemm.cu", []),
     ("jmid_attn.cu", []),
     ("jmid_api.cu", []),
+    ("pred_prep.cu", ["-fmad=false", "-Xcompiler", "-ffp-contract=off"]),
+    ("pred_encode.cu", []),
+    ("pred_post.cu", []),
+    ("pred_api.cu", []),
 ]
 
 

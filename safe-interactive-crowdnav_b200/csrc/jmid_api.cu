@@ -20,7 +20,7 @@ struct LayerDev {
 };
 
 struct Plans {
-    int n_env = 0, M = 0;
+    int n_env = 0, M = 0, A = 0, N = 0; // A agents per env in this call (<= the handle's A), N = A*S*T tokens per env
     GemmPlan qkv[NL], out[NL], ff1[NL], ff2[NL], c3, c4;
     AttnPlan attn;
 };
@@ -40,11 +40,11 @@ struct SnbJmid {
     bf16 *h, *y, *qkv, *att, *ff, *t3, *t4;
     bf16 *pre;
     float *xa, *xb, *gc, *bc, *gate, *hb;
-    std::map<int, Plans> plans;
-    // CUDA graphs of one chunk's whole DDIM loop, keyed by (envs in chunk, n_steps); captured on second use
+    std::map<std::pair<int, int>, Plans> plans; // keyed by (envs in chunk, agents per env)
+    // CUDA graphs of one chunk's whole DDIM loop, keyed by (envs in chunk, agents per env, n_steps); captured on second use
     float *ctx_stage = nullptr;
-    std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
-    std::map<std::pair<int, int>, int> graph_uses;
+    std::map<int64_t, cudaGraphExec_t> graphs;
+    std::map<int64_t, int> graph_uses;
     int use_graphs = 1;
     cudaStream_t own_stream = nullptr;
     // host-call staging
@@ -81,13 +81,16 @@ int dup_bf16(SnbJmid *h, bf16 **dst, const float *src, size_t n, cudaStream_t s)
     return snb_k_f32_to_bf16(src, *dst, n, s);
 }
 
-int get_plans(SnbJmid *h, int n_env, Plans **out)
+int get_plans(SnbJmid *h, int n_env, int A, Plans **out)
 {
-    auto it = h->plans.find(n_env);
+    const std::pair<int, int> key(n_env, A);
+    auto it = h->plans.find(key);
     if (it != h->plans.end()) { *out = &it->second; return SNB_OK; }
     Plans p;
     p.n_env = n_env;
-    p.M = n_env * h->N;
+    p.A = A;
+    p.N = A * h->S * h->T;
+    p.M = n_env * p.N;
     int rc = 0;
     for (int l = 0; l < NL && !rc; ++l) {
         rc = snb_gemm_plan(&p.qkv[l], h->h, h->L[l].wqkv, h->qkv, 0, p.M, 3 * D, D);
@@ -97,20 +100,20 @@ int get_plans(SnbJmid *h, int n_env, Plans **out)
     }
     if (!rc) rc = snb_gemm_plan(&p.c3, h->h, h->wc3, h->t3, 0, p.M, 256, D);
     if (!rc) rc = snb_gemm_plan(&p.c4, h->t3, h->wc4, h->t4, 0, p.M, 128, 256);
-    if (!rc && h->joint) rc = snb_attn_plan(&p.attn, h->qkv, n_env, h->N);
+    if (!rc && h->joint) rc = snb_attn_plan(&p.attn, h->qkv, n_env, p.N);
     if (rc) return rc;
-    h->plans[n_env] = p;
-    *out = &h->plans[n_env];
+    h->plans[key] = p;
+    *out = &h->plans[key];
     return SNB_OK;
 }
 
 // one noise-network forward for the chunk currently staged in h->gc / h->bc / x_in (diffusion.py:173-209)
 int net_forward(SnbJmid *h, Plans *P, const float *x_in, float *x_next, float *eps_out, int t, int t_next, cudaStream_t s)
 {
-    const int M = P->M, n_ba = P->n_env * h->A;
+    const int M = P->M, n_ba = P->n_env * P->A;
     int rc = snb_k_hyper_iter(h->hyper, h->gc, h->bc, h->gate, h->hb, n_ba, h->betas[t], s);
     if (rc) return rc;
-    rc = snb_k_embed(x_in, h->c1_w, h->c1_b, h->gate, h->hb, h->pe, h->h, M, h->N, h->T, h->A, s);
+    rc = snb_k_embed(x_in, h->c1_w, h->c1_b, h->gate, h->hb, h->pe, h->h, M, P->N, h->T, P->A, s);
     if (rc) return rc;
     GemmEpi e;
     for (int l = 0; l < NL; ++l) {
@@ -131,14 +134,14 @@ int net_forward(SnbJmid *h, Plans *P, const float *x_in, float *x_next, float *e
     }
     memset(&e, 0, sizeof(e));
     e.bias = h->c3_b; e.gate = h->gate + 512; e.hbias = h->hb + 512; e.tab_ld = HYPER_LD;
-    e.tok_per_env = h->N; e.T = h->T; e.A = h->A;
+    e.tok_per_env = P->N; e.T = h->T; e.A = P->A;
     if ((rc = snb_gemm_launch(&P->c3, EPI_CSL_BF16, &e, h->num_sms, s))) return rc;
     e.bias = h->c4_b; e.gate = h->gate + 768; e.hbias = h->hb + 768;
     if ((rc = snb_gemm_launch(&P->c4, EPI_CSL_BF16, &e, h->num_sms, s))) return rc;
     // DDIM coefficients in fp32 like torch: (1 - ab).sqrt(), ab.sqrt(), ab_next.sqrt(), (1 - ab_next).sqrt()
     const float ab = h->alpha_bars[t], abn = h->alpha_bars[t_next];
-    return snb_k_tail_ddim(h->t4, h->lin_w, h->lin_b, h->gate + 896, h->hb + 896, HYPER_LD, x_in, x_next, eps_out, M, h->N, h->T,
-                           h->A, sqrtf(1.0f - ab), sqrtf(ab), sqrtf(abn), sqrtf(1.0f - abn), s);
+    return snb_k_tail_ddim(h->t4, h->lin_w, h->lin_b, h->gate + 896, h->hb + 896, HYPER_LD, x_in, x_next, eps_out, M, P->N, h->T,
+                           P->A, sqrtf(1.0f - ab), sqrtf(ab), sqrtf(abn), sqrtf(1.0f - abn), s);
 }
 
 } // namespace
@@ -252,7 +255,7 @@ namespace {
 int chunk_sequence(SnbJmid *h, Plans *P, int n_steps, cudaStream_t s, float **result)
 {
     const int stride = 100 / n_steps; // int(100 / step), diffusion.py:507
-    int rc = snb_k_hyper_ctx(h->hyper, h->ctx_stage, h->gc, h->bc, P->n_env * h->A, s);
+    int rc = snb_k_hyper_ctx(h->hyper, h->ctx_stage, h->gc, h->bc, P->n_env * P->A, s);
     if (rc) return rc;
     float *cur = h->xa, *nxt = h->xb;
     for (int t = 100; t > 0; t -= stride) {
@@ -264,23 +267,29 @@ int chunk_sequence(SnbJmid *h, Plans *P, int n_steps, cudaStream_t s, float **re
 }
 } // namespace
 
-extern "C" int snb_jmid_denoise(SnbJmid *h, const float *ctx, const float *x_T, float *out_vel, int32_t B, int32_t n_steps, void *stream)
+extern "C" int snb_jmid_denoise_agents(SnbJmid *h, const float *ctx, const float *x_T, float *out_vel, int32_t B, int32_t A,
+                                       int32_t n_steps, void *stream)
 {
     SNB_REQUIRE(h && ctx && x_T && out_vel, SNB_EINVAL, "snb_jmid_denoise: NULL argument");
     SNB_REQUIRE(B >= 0 && n_steps >= 1 && n_steps <= 100, SNB_EINVAL, "snb_jmid_denoise: bad B / n_steps");
+    SNB_REQUIRE(A >= 1 && A <= h->A, SNB_EINVAL, "snb_jmid_denoise: A=%d outside [1, %d] (the handle's agent capacity)", A, h->A);
     cudaStream_t s = (cudaStream_t)stream;
     const int stride = 100 / n_steps;
     const int n_iter = (100 + stride - 1) / stride;
-    for (int e0 = 0; e0 < B; e0 += h->chunk_envs) {
-        const int ne = (B - e0) < h->chunk_envs ? (B - e0) : h->chunk_envs;
+    const int N = A * h->S * h->T;
+    // a chunk is bounded by ROWS (chunk_envs * tokens at full A): fewer agents per env -> more envs per chunk
+    int chunk = (int)(((size_t)h->chunk_envs * h->N) / N);
+    if (chunk < 1) chunk = 1;
+    for (int e0 = 0; e0 < B; e0 += chunk) {
+        const int ne = (B - e0) < chunk ? (B - e0) : chunk;
         Plans *P = nullptr;
-        int rc = get_plans(h, ne, &P);
+        int rc = get_plans(h, ne, A, &P);
         if (rc) return rc;
         const size_t M = (size_t)P->M;
-        SNB_CUDA_TRY(cudaMemcpyAsync(h->ctx_stage, ctx + (size_t)e0 * h->A * 256, (size_t)ne * h->A * 256 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        SNB_CUDA_TRY(cudaMemcpyAsync(h->xa, x_T + (size_t)e0 * h->N * 2, M * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        SNB_CUDA_TRY(cudaMemcpyAsync(h->ctx_stage, ctx + (size_t)e0 * A * 256, (size_t)ne * A * 256 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        SNB_CUDA_TRY(cudaMemcpyAsync(h->xa, x_T + (size_t)e0 * N * 2, M * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
         float *result = (n_iter & 1) ? h->xb : h->xa;
-        const std::pair<int, int> key(ne, n_steps);
+        const int64_t key = ((int64_t)ne << 24) | ((int64_t)A << 8) | (int64_t)n_steps;
         auto git = h->graphs.find(key);
         if (git != h->graphs.end()) {
             SNB_CUDA_TRY(cudaGraphLaunch(git->second, s));
@@ -307,8 +316,24 @@ extern "C" int snb_jmid_denoise(SnbJmid *h, const float *ctx, const float *x_T, 
             if ((rc = chunk_sequence(h, P, n_steps, s, &res2))) return rc;
             result = res2;
         }
-        SNB_CUDA_TRY(cudaMemcpyAsync(out_vel + (size_t)e0 * h->N * 2, result, M * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        SNB_CUDA_TRY(cudaMemcpyAsync(out_vel + (size_t)e0 * N * 2, result, M * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
+    return SNB_OK;
+}
+
+extern "C" int snb_jmid_denoise(SnbJmid *h, const float *ctx, const float *x_T, float *out_vel, int32_t B, int32_t n_steps, void *stream)
+{
+    SNB_REQUIRE(h, SNB_EINVAL, "snb_jmid_denoise: NULL handle");
+    return snb_jmid_denoise_agents(h, ctx, x_T, out_vel, B, h->A, n_steps, stream);
+}
+
+extern "C" int snb_jmid_dims(const SnbJmid *h, int32_t *A, int32_t *S, int32_t *T, int32_t *joint)
+{
+    SNB_REQUIRE(h, SNB_EINVAL, "snb_jmid_dims: NULL handle");
+    if (A) *A = h->A;
+    if (S) *S = h->S;
+    if (T) *T = h->T;
+    if (joint) *joint = h->joint;
     return SNB_OK;
 }
 
@@ -320,7 +345,7 @@ extern "C" int snb_jmid_eps(SnbJmid *h, const float *ctx, const float *x_t, floa
     for (int e0 = 0; e0 < B; e0 += h->chunk_envs) {
         const int ne = (B - e0) < h->chunk_envs ? (B - e0) : h->chunk_envs;
         Plans *P = nullptr;
-        int rc = get_plans(h, ne, &P);
+        int rc = get_plans(h, ne, h->A, &P);
         if (rc) return rc;
         if ((rc = snb_k_hyper_ctx(h->hyper, ctx + (size_t)e0 * h->A * 256, h->gc, h->bc, ne * h->A, s))) return rc;
         if ((rc = net_forward(h, P, x_t + (size_t)e0 * h->N * 2, nullptr, eps + (size_t)e0 * h->N * 2, t, t - 1, s))) return rc;

@@ -68,6 +68,15 @@ class JmidWeights(C.Structure):
                 ("layers", EncLayerWeights * 3), ("pos_emb", _vp), ("betas", _vp), ("alpha_bars", _vp)]
 
 
+class LstmWeights(C.Structure):
+    _fields_ = [(n, _vp) for n in ("w_ih", "w_hh", "b_ih", "b_hh")]
+
+
+class EncoderWeights(C.Structure):
+    _fields_ = [("node_history", LstmWeights), ("edge_ped", LstmWeights), ("edge_robot", LstmWeights),
+                ("att_w1", _vp), ("att_w2", _vp), ("att_v", _vp)]
+
+
 def _proto(name, restype, argtypes, required=True):
     try:
         f = getattr(lib, name)
@@ -102,6 +111,21 @@ _proto("snb_jmid_predict_host", C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C
 _proto("snb_jmid_gemm_bf16", C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp], required=False)
 _proto("snb_jmid_attention", C.c_int, [_vp, _vp, _i32, _i32, _vp], required=False)
 _proto("snb_jmid_flops_per_iter", _d, [_i32, _i32, _i32, _i32], required=False)
+_proto("snb_jmid_denoise_agents", C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp], required=False)
+_proto("snb_jmid_dims", C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)], required=False)
+_u64 = C.c_uint64
+_proto("snb_pred_create", C.c_int, [C.POINTER(_vp), C.POINTER(EncoderWeights), _vp, _i32, _i32, _vp], required=False)
+_proto("snb_pred_destroy", C.c_int, [_vp], required=False)
+_proto("snb_pred_push_history", C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp], required=False)
+_proto("snb_pred_reset_history", C.c_int, [_vp], required=False)
+_proto("snb_pred_set_history", C.c_int, [_vp, _vp, _vp, _i32, _vp], required=False)
+_proto("snb_pred_encode", C.c_int, [_vp, _i32, _d, _d, _vp, _vp, _vp, _vp, _vp], required=False)
+_proto("snb_pred_noise", C.c_int, [_vp, C.c_int64, _u64, _u64, _vp], required=False)
+_proto("snb_pred_predict", C.c_int, [_vp, _i32, _vp, _u64, _i32, _i32, _d, _d, _vp, _vp, _vp], required=False)
+_proto("snb_pred_predict_host", C.c_int, [_vp, C.POINTER(_d), C.POINTER(_d), _i32, C.POINTER(C.c_float), _u64, _i32, _i32, _d, _d,
+                                           C.POINTER(_d), C.POINTER(_d)], required=False)
+_proto("snb_pred_kde_topk", C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp], required=False)
+_proto("snb_pred_ingest", C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _d, _i32, _vp, _vp, _vp, _vp, _vp], required=False)
 
 
 def check(rc, what=""):

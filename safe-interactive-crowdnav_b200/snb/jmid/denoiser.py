@@ -88,13 +88,16 @@ class JmidDenoiser:
         assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == tuple(shape), (t.shape, shape)
 
     def denoise(self, ctx, x_T, n_steps=20, out=None, stream=None):
-        """ctx [B,A,256], x_T [B,S*A,T,2] (row r = s*A + a) -> velocities [B,S,A,T,2] (all fp32 CUDA)."""
-        B = ctx.shape[0]
-        self._chk(ctx, (B, self.A, 256)); self._chk(x_T, (B, self.S * self.A, self.T, 2))
+        """ctx [B,A',256], x_T [B,S*A',T,2] (row r = s*A' + a) -> velocities [B,S,A',T,2] (all fp32 CUDA); A' <= A, the
+        number of agents of this call (the attention cluster of the predictor changes size from step to step)."""
+        B, A = ctx.shape[0], ctx.shape[1]
+        if not 1 <= A <= self.A:
+            raise _capi.SnbError(f"denoise: {A} agents per environment, the handle was built for at most {self.A}")
+        self._chk(ctx, (B, A, 256)); self._chk(x_T, (B, self.S * A, self.T, 2))
         if out is None:
-            out = torch.empty(B, self.S, self.A, self.T, 2, dtype=torch.float32, device=self.device)
-        _capi.check(_capi.lib.snb_jmid_denoise(self._h, _capi.ptr(ctx), _capi.ptr(x_T), _capi.ptr(out), B, int(n_steps),
-                                               _capi.stream_ptr(stream)), "snb_jmid_denoise")
+            out = torch.empty(B, self.S, A, self.T, 2, dtype=torch.float32, device=self.device)
+        _capi.check(_capi.lib.snb_jmid_denoise_agents(self._h, _capi.ptr(ctx), _capi.ptr(x_T), _capi.ptr(out), B, A, int(n_steps),
+                                                      _capi.stream_ptr(stream)), "snb_jmid_denoise")
         return out
 
     def eps(self, ctx, x_t, t, stream=None):
@@ -108,10 +111,10 @@ class JmidDenoiser:
 
     def integrate(self, vel, p0, dt=0.25, stream=None):
         """vel [B,S,A,T,2], p0 [B,A,2] -> positions [B,S,A,T,2] (SingleIntegrator.integrate_samples)."""
-        B = vel.shape[0]
-        self._chk(vel, (B, self.S, self.A, self.T, 2)); self._chk(p0, (B, self.A, 2))
+        B, A = vel.shape[0], vel.shape[2]
+        self._chk(vel, (B, self.S, A, self.T, 2)); self._chk(p0, (B, A, 2))
         pos = torch.empty_like(vel)
-        _capi.check(_capi.lib.snb_jmid_integrate(_capi.ptr(vel), _capi.ptr(p0), _capi.ptr(pos), B, self.S, self.A, self.T,
+        _capi.check(_capi.lib.snb_jmid_integrate(_capi.ptr(vel), _capi.ptr(p0), _capi.ptr(pos), B, self.S, A, self.T,
                                                  float(dt), _capi.stream_ptr(stream)), "snb_jmid_integrate")
         return pos
 
