@@ -186,11 +186,11 @@ def most_likely_samples(forecasts, k):
     return forecasts[top].permute(1, 0, 2, 3), lw.unsqueeze(0).expand(A, k)
 
 
-def predict_ret_best(enc_w, ddpm_w, hist, robot_hist, x_T, num_draw, num_ret, step, dt=0.25, horizon=8, joint=True):
+def predict_ret_best(enc_w, ddpm_w, hist, robot_hist, x_T, num_draw, num_ret, step, dt=0.25, horizon=8, joint=True, radius=3.0):
     """HumanTrajectoryForecasterSim.predict_ret_best (mid_sim_wrapper.py:482-509) with injected noise x_T [S*A,T,2].
     Returns (forecasts [H,k,T+1,2] float64, logw [H,k] float64, ctx [A,256])."""
     H = hist.shape[0]
-    inp = encoder_inputs(hist, robot_hist, dt)
+    inp = encoder_inputs(hist, robot_hist, dt, radius)
     ctx = encode(enc_w, inp)
     vel = JO.sample(ddpm_w, ctx, x_T, step=step, joint=joint)                       # [S,A,T,2]
     pos = JO.integrate(vel, torch.tensor(inp["p0"], dtype=torch.float32), dt)       # ascending human id == sort by node id
