@@ -17,7 +17,7 @@ OUT = os.path.join(OUT_DIR, "libsnb.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("SNB_NVCC_FLAGS", "").split()
 
 UNITS = [
     ("snb_api.cu", []),
