@@ -3,16 +3,8 @@
 // The reference flattens the T*A*S tokens of one environment into ONE unmasked sequence and runs
 // nn.MultiheadAttention(d=512, heads=4) over it (models/diffusion.py:196-204, quirk q1).  This kernel computes, per
 // (environment, head, 128-query tile):  O = softmax(Q K^T / sqrt(128)) V  flash-style, never materialising the
-// N x N score matrix in HBM:
-//   warp 0      TMA producer: Q tile once, then K / V blocks of 128 keys through 2-stage smem rings
-//   warp 1      MMA issuer:   S = Q K^T (SS, M=128 N<=128 K=128) into a double-buffered TMEM S tile,
-//                             O += P V (TS: P read from TMEM as bf16, V MN-major from smem) into a TMEM O tile
-//   warp 2      TMEM allocator
-//   warps 4..7  softmax:      one thread per query row: tcgen05.ld the S row, running max with lazy rescale of O,
-//                             exp2, bf16 P written back over S with tcgen05.st, final O / l -> global
-// S(j+1) is issued before waiting for P(j), so the QK^T of the next block overlaps the softmax of the current one.
+// N x N score matrix in HBM.  Structure and measurements: see the comment above attn_fwd_kernel.
 #include <cfloat>
-#include <cstdlib>
 #include <mutex>
 
 #include "jmid_internal.h"
@@ -22,14 +14,11 @@ namespace {
 
 constexpr int HD = 128;       // head dim
 constexpr int NHEAD = 4;
-constexpr int BQ = 128;       // queries per CTA
+constexpr int BQ = 128;       // queries per tile (two tiles per CTA)
 constexpr int BKV = 128;      // keys per block
-constexpr int KV_STAGES = 2;
 constexpr int TILE_BYTES = BQ * HD * 2; // 32 KB: two 64-column boxes of 16 KB
-constexpr int ATTN_THREADS = 256;
-constexpr int ATTN_SMEM = TILE_BYTES * (1 + 2 * KV_STAGES) + 1024 + 256;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O = 256;
+constexpr uint32_t TM_S = 0, TM_O = 256;  // + 128 * tile
 constexpr float RESCALE_THRESHOLD = 8.0f; // log2 units: P <= 2^8 before the running max is refreshed
 
 struct AttnArgs {
@@ -37,252 +26,6 @@ struct AttnArgs {
     int n_tok;
     float scale_log2; // log2(e) / sqrt(HD)
 };
-
-__global__ void __launch_bounds__(ATTN_THREADS, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
-{
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *sQ = smem;
-    uint8_t *sK = smem + TILE_BYTES;
-    uint8_t *sV = smem + TILE_BYTES * (1 + KV_STAGES);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TILE_BYTES * (1 + 2 * KV_STAGES));
-    uint64_t *q_full = bars;
-    uint64_t *k_full = bars + 1, *k_empty = bars + 3, *v_full = bars + 5, *v_empty = bars + 7;
-    uint64_t *s_full = bars + 9, *p_ready = bars + 11, *pv_done = bars + 13;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 15);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * BQ, head = blockIdx.y, env = blockIdx.z;
-    const int n_tok = args.n_tok;
-    const int n_kv = (n_tok + BKV - 1) / BKV;
-
-    if (warp == 0 && lane == 0) {
-        tc::prefetch_tmap(&tmQKV);
-        tc::mbar_init(q_full, 1);
-        for (int s = 0; s < 2; ++s) {
-            tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1);
-            tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], 1);
-            tc::mbar_init(&s_full[s], 1); tc::mbar_init(&p_ready[s], 128); tc::mbar_init(&pv_done[s], 1);
-        }
-        tc::fence_barrier_init();
-    }
-    if (warp == 2) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            const int cq = head * HD, ck = 512 + head * HD, cv = 1024 + head * HD;
-            tc::mbar_arrive_expect_tx(q_full, TILE_BYTES);
-            tc::tma_load_3d(sQ, &tmQKV, q_full, cq, q0, env);
-            tc::tma_load_3d(sQ + TILE_BYTES / 2, &tmQKV, q_full, cq + 64, q0, env);
-            for (int j = 0; j < n_kv; ++j) {
-                const int st = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                tc::mbar_wait(&k_empty[st], ph ^ 1);
-                tc::mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
-                tc::tma_load_3d(sK + st * TILE_BYTES, &tmQKV, &k_full[st], ck, j * BKV, env);
-                tc::tma_load_3d(sK + st * TILE_BYTES + TILE_BYTES / 2, &tmQKV, &k_full[st], ck + 64, j * BKV, env);
-                tc::mbar_wait(&v_empty[st], ph ^ 1);
-                tc::mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
-                tc::tma_load_3d(sV + st * TILE_BYTES, &tmQKV, &v_full[st], cv, j * BKV, env);
-                tc::tma_load_3d(sV + st * TILE_BYTES + TILE_BYTES / 2, &tmQKV, &v_full[st], cv + 64, j * BKV, env);
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t q_addr = tc::smem_u32(sQ);
-            auto kv_cols = [&](int j) { // keys of block j rounded up to the UMMA N granularity (16)
-                const int rem = n_tok - j * BKV;
-                return rem >= BKV ? BKV : ((rem + 15) & ~15);
-            };
-            auto issue_S = [&](int j) {
-                const int st = j & 1;
-                tc::mbar_wait(&k_full[st], (j >> 1) & 1);
-                tc::tc_fence_after();
-                const uint32_t k_addr = tc::smem_u32(sK + st * TILE_BYTES);
-                const uint32_t idesc = tc::make_idesc_bf16(BQ, (uint32_t)kv_cols(j), 0, 0);
-                const uint32_t d = tmem_base + (st ? TM_S1 : TM_S0);
-#pragma unroll
-                for (int k = 0; k < HD / 16; ++k) {
-                    const uint32_t off = (k >> 2) * (TILE_BYTES / 2) + (k & 3) * 32;
-                    tc::umma_ss(d, tc::make_smem_desc_sw128(q_addr + off, 16, 1024), tc::make_smem_desc_sw128(k_addr + off, 16, 1024),
-                                idesc, k != 0 ? 1u : 0u);
-                }
-                tc::umma_commit(&k_empty[st]);
-                tc::umma_commit(&s_full[st]);
-            };
-            tc::mbar_wait(q_full, 0);
-            tc::tc_fence_after();
-            issue_S(0);
-            constexpr uint32_t idesc_pv = tc::make_idesc_bf16(BQ, HD, 0, 1); // B = V is MN-major (head dim contiguous)
-            for (int j = 0; j < n_kv; ++j) {
-                const int st = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                if (j + 1 < n_kv) issue_S(j + 1);
-                tc::mbar_wait(&p_ready[st], ph);
-                tc::mbar_wait(&v_full[st], ph);
-                tc::tc_fence_after();
-                const uint32_t v_addr = tc::smem_u32(sV + st * TILE_BYTES);
-                const uint32_t p_tmem = tmem_base + (st ? TM_S1 : TM_S0);
-                const int ksteps = kv_cols(j) / 16;
-                for (int k = 0; k < ksteps; ++k) {
-                    // 16 keys = 2 groups of 8 rows (SBO 1024 B); the two 64-wide head-dim boxes are LBO = 16 KB apart
-                    const uint64_t dv = tc::make_smem_desc_sw128(v_addr + k * 2048, TILE_BYTES / 2, 1024);
-                    tc::umma_ts(tmem_base + TM_O, p_tmem + k * 8, dv, idesc_pv, (j | k) != 0 ? 1u : 0u);
-                }
-                tc::umma_commit(&v_empty[st]);
-                tc::umma_commit(&pv_done[st]);
-            }
-        }
-    } else if (warp >= 4) {
-        // ===================== softmax / correction / epilogue =====================
-        const int quarter = warp & 3;
-        const int row_in_tile = quarter * 32 + lane;
-        const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
-        const float c = args.scale_log2;
-        float m_used = -INFINITY; // running max the exponents are taken against (raw score units)
-        float l = 0.0f;
-        for (int j = 0; j < n_kv; ++j) {
-            const int st = j & 1;
-            const uint32_t ph = (j >> 1) & 1;
-            tc::mbar_wait(&s_full[st], ph);
-            __syncwarp();                 // reconverge before the .sync.aligned TMEM loads
-            tc::tc_fence_after();
-            const uint32_t s_addr = tmem_base + lane_addr + (st ? TM_S1 : TM_S0);
-            // the whole S row: four 32-column loads in flight, ONE tcgen05.wait::ld
-            uint32_t s0[32], s1[32], s2[32], s3[32];
-            tc::tmem_ld_32x32(s_addr, s0);
-            tc::tmem_ld_32x32(s_addr + 32, s1);
-            tc::tmem_ld_32x32(s_addr + 64, s2);
-            tc::tmem_ld_32x32(s_addr + 96, s3);
-            tc::tmem_ld_wait();
-            const int valid = n_tok - j * BKV; // keys of this block that exist
-            if (valid < BKV) {                 // ragged last block: keys that do not exist score -inf
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (i >= valid) s0[i] = 0xff800000u;
-                    if (32 + i >= valid) s1[i] = 0xff800000u;
-                    if (64 + i >= valid) s2[i] = 0xff800000u;
-                    if (96 + i >= valid) s3[i] = 0xff800000u;
-                }
-            }
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                mx0 = fmaxf(mx0, __uint_as_float(s0[i])); mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
-                mx2 = fmaxf(mx2, __uint_as_float(s2[i])); mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
-            }
-            const float bmax = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-            if (j == 0) {
-                m_used = bmax;
-            } else if (__any_sync(0xffffffffu, (bmax - m_used) * c > RESCALE_THRESHOLD)) {
-                // Refresh the running max.  The decision is WARP-uniform (tcgen05.ld/st are .sync.aligned and must be
-                // executed by all 32 lanes together); lanes whose own max did not grow rescale by exactly 1.
-                const int pst = (j - 1) & 1;
-                tc::mbar_wait(&pv_done[pst], ((j - 1) >> 1) & 1);     // O is stable once the previous PV has landed
-                __syncwarp();
-                tc::tc_fence_after();
-                const float m_new = fmaxf(m_used, bmax);
-                const float f = tc::ex2_approx((m_used - m_new) * c);
-                const uint32_t o_addr = tmem_base + lane_addr + TM_O;
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t r[32];
-                    tc::tmem_ld_32x32(o_addr + ch * 32, r);
-                    tc::tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-                    tc::tmem_st_32x32(o_addr + ch * 32, r);
-                }
-                l *= f;
-                m_used = m_new;
-            }
-            const float mc = m_used * c;
-            float sum0 = 0.0f, sum1 = 0.0f, sum2 = 0.0f, sum3 = 0.0f;
-            {
-                uint32_t pk[32];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float a0 = tc::ex2_approx(fmaf(__uint_as_float(s0[2 * i]), c, -mc)), a1 = tc::ex2_approx(fmaf(__uint_as_float(s0[2 * i + 1]), c, -mc));
-                    const float b0 = tc::ex2_approx(fmaf(__uint_as_float(s1[2 * i]), c, -mc)), b1 = tc::ex2_approx(fmaf(__uint_as_float(s1[2 * i + 1]), c, -mc));
-                    sum0 += a0; sum1 += a1; sum2 += b0; sum3 += b1;
-                    pk[i] = tc::pack_bf16(a0, a1); pk[16 + i] = tc::pack_bf16(b0, b1);
-                }
-                tc::tmem_st_32x32(s_addr, pk);          // P columns [0,32)  <- S columns [0,64)
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float a0 = tc::ex2_approx(fmaf(__uint_as_float(s2[2 * i]), c, -mc)), a1 = tc::ex2_approx(fmaf(__uint_as_float(s2[2 * i + 1]), c, -mc));
-                    const float b0 = tc::ex2_approx(fmaf(__uint_as_float(s3[2 * i]), c, -mc)), b1 = tc::ex2_approx(fmaf(__uint_as_float(s3[2 * i + 1]), c, -mc));
-                    sum0 += a0; sum1 += a1; sum2 += b0; sum3 += b1;
-                    pk[i] = tc::pack_bf16(a0, a1); pk[16 + i] = tc::pack_bf16(b0, b1);
-                }
-                tc::tmem_st_32x32(s_addr + 32, pk);     // P columns [32,64) <- S columns [64,128)
-            }
-            l += (sum0 + sum1) + (sum2 + sum3);
-            tc::tmem_st_wait();
-            tc::tc_fence_before();
-            tc::mbar_arrive(&p_ready[st]);
-        }
-        // final: O / l -> global
-        const int lst = (n_kv - 1) & 1;
-        tc::mbar_wait(&pv_done[lst], ((n_kv - 1) >> 1) & 1);
-        __syncwarp();
-        tc::tc_fence_after();
-        const float inv_l = 1.0f / l;
-        const int row = q0 + row_in_tile;
-        const uint32_t o_addr = tmem_base + lane_addr + TM_O;
-        bf16 *dst = args.out + ((size_t)env * n_tok + row) * (NHEAD * HD) + head * HD;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-            uint32_t r[32];
-            tc::tmem_ld_32x32(o_addr + ch * 32, r);
-            tc::tmem_ld_wait();
-            if (row < n_tok) {
-                uint4 *o4 = reinterpret_cast<uint4 *>(dst + ch * 32);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint4 o;
-                    o.x = tc::pack_bf16(__uint_as_float(r[8 * q + 0]) * inv_l, __uint_as_float(r[8 * q + 1]) * inv_l);
-                    o.y = tc::pack_bf16(__uint_as_float(r[8 * q + 2]) * inv_l, __uint_as_float(r[8 * q + 3]) * inv_l);
-                    o.z = tc::pack_bf16(__uint_as_float(r[8 * q + 4]) * inv_l, __uint_as_float(r[8 * q + 5]) * inv_l);
-                    o.w = tc::pack_bf16(__uint_as_float(r[8 * q + 6]) * inv_l, __uint_as_float(r[8 * q + 7]) * inv_l);
-                    o4[q] = o;
-                }
-            }
-        }
-        tc::tc_fence_before();
-    }
-    __syncthreads();
-    if (warp == 2) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// attn_fwd2_kernel: TWO 128-query tiles (A, B) of one (environment, head) per CTA, ping-ponged through the tensor pipe:
-//   warp 0        TMA producer: Q_A, Q_B once, then K / V blocks of 128 keys through 2-stage rings (each K / V block is
-//                 staged ONCE for both tiles)
-//   warp 1        MMA issuer, per key block j:  O_A += P_A(j) V(j); S_A(j+1) = Q_A K(j+1)^T; O_B += P_B(j) V(j);
-//                 S_B(j+1) = Q_B K(j+1)^T.  tcgen05.mma executes in issue order, so S_t(j+1) may overwrite the TMEM
-//                 columns P_t(j) lives in right behind the PV that reads them.
-//   warp 2        TMEM allocator (all 512 columns: S_A 0-127, S_B 128-255, O_A 256-383, O_B 384-511)
-//   warps 4..11   softmax of tile A, warps 12..19 softmax of tile B.  TWO threads per query row (warps w and w+4 own the
-//                 same 32 TMEM lanes; one takes key columns 0-63 of the block, the other 64-127): tcgen05.ld the half
-//                 row, block max exchanged through shared memory + a 64-thread named barrier, running max with lazy
-//                 rescale of O, exp2, bf16 P written over S, final O / l -> global.
-// While the softmax warps of one tile work on block j, the tensor pipe runs the other tile's PV(j) + S(j+1).  One warp per
-// scheduler only reaches about half of the MUFU rate (measured: r01c ncu capture, xu pipe 44 %), hence two warps per
-// scheduler and tile: the MUFU pipe (16 ex2 / clk / SM = 1024 clk per 128x128 block) and the tensor pipe (2 x 512 clk per
-// block) can both stay busy.
-// Registers: 640 threads x 96 at launch; warps 0-3 shrink to 64 and the softmax warps grow to 104 (setmaxnreg).
-constexpr int ATTN2_THREADS = 640;
-constexpr int ATTN2_XCH_FLOATS = 2 * 2 * 2 * 128;       // [slot][tile][half][row]
-constexpr int ATTN2_SMEM = TILE_BYTES * (2 + 2 * KV_STAGES) + 1024 + 256 + ATTN2_XCH_FLOATS * 4;
-constexpr uint32_t TM2_S = 0, TM2_O = 256; // + 128 * tile
 
 #ifdef SNB_ATTN_TRACE
 // debug build only (SNB_NVCC_FLAGS=-DSNB_ATTN_TRACE): clock64() stamps of CTA (0,0,0): [role 0..4][block j < 16][event < 8]
@@ -295,20 +38,41 @@ __device__ long long g_attn_trace[6 * 16 * 8];
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
-__global__ void __launch_bounds__(ATTN2_THREADS, 1)
-attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
+// ---------------------------------------------------------------------------------------------------------------------
+// attn_fwd_kernel: softmax decoupled from the tensor pipe.  Two 128-query tiles (A, B) of one (environment, head) per CTA.
+//   warp 0        TMA producer: Q_A, Q_B, then K / V blocks of 128 keys through ONE 3-slot ring in consumption order
+//                 K0, K1, V0, K2, V1, ...
+//   warp 1        MMA issuer.  S_t = Q_t K^T (SS) into TMEM; O_t += P_t V (SS: P_t comes from SHARED memory).  Because P does
+//                 not overlay S, S_t(j+1) is issued as soon as the softmax warps have pulled S_t(j) into registers -- long
+//                 before P_t(j) exists -- so the softmax warps never wait for the tensor pipe and the only serial chain left
+//                 is softmax(j) -> softmax(j+1) (measured with the clock64 trace: the aliased-P variant spent 40 % of every
+//                 block waiting for S).
+//   warp 2        TMEM allocator (S_A 0-127, S_B 128-255, O_A 256-383, O_B 384-511)
+//   warps 4..7    softmax of tile A, warps 8..11 of tile B; one thread per query row (no shuffles): tcgen05.ld the S row,
+//                 release S, running max with lazy rescale of O, exp2, bf16 P row -> 128B-swizzled shared memory
+//                 (the K-major A operand layout TMA would have produced), final O / l -> global.
+// Registers: 384 threads x 168 at launch; warps 0-3 shrink to 88, the softmax warps grow to 208 (setmaxnreg).
+#ifndef SNB_ATTN_POLY_EVERY
+#define SNB_ATTN_POLY_EVERY 4
+#endif
+constexpr int ATTN_THREADS = 384;
+constexpr int ATTN_RING = 3;
+constexpr int ATTN_SMEM = TILE_BYTES * (2 + 2 + ATTN_RING) + 1024 + 256;
+
+__global__ void __launch_bounds__(ATTN_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
 {
+    constexpr int POLY_EVERY = SNB_ATTN_POLY_EVERY;   // one key pair in POLY_EVERY gets its 2^x from the FMA pipe (0 = none)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sQ = smem;                                    // 2 tiles
-    uint8_t *sK = smem + TILE_BYTES * 2;                   // KV_STAGES
-    uint8_t *sV = smem + TILE_BYTES * (2 + KV_STAGES);     // KV_STAGES
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TILE_BYTES * (2 + 2 * KV_STAGES));
+    uint8_t *sP = smem + TILE_BYTES * 2;                   // 2 tiles
+    uint8_t *sKV = smem + TILE_BYTES * 4;                  // ring of ATTN_RING tiles
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TILE_BYTES * (4 + ATTN_RING));
     uint64_t *q_full = bars;                               // [2] per tile
-    uint64_t *k_full = bars + 2, *k_empty = bars + 4, *v_full = bars + 6, *v_empty = bars + 8;   // [2] per stage
-    uint64_t *s_full = bars + 10, *p_ready = bars + 12, *pv_done = bars + 14;                    // [2] per tile
+    uint64_t *kv_full = bars + 2, *kv_empty = bars + 5;    // [3] per ring slot
+    uint64_t *s_full = bars + 8, *s_free = bars + 10, *p_ready = bars + 12, *pv_done = bars + 14;   // [2] per tile
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
-    float *xch = reinterpret_cast<float *>(bars + 32);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int q0 = blockIdx.x * (2 * BQ), head = blockIdx.y, env = blockIdx.z;
@@ -327,23 +91,21 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
         tc::prefetch_tmap(&tmQKV);
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(&q_full[s], 1);
-            tc::mbar_init(&k_full[s], 1); tc::mbar_init(&k_empty[s], 1);
-            tc::mbar_init(&v_full[s], 1); tc::mbar_init(&v_empty[s], 1);
-            tc::mbar_init(&s_full[s], 1); tc::mbar_init(&p_ready[s], 256); tc::mbar_init(&pv_done[s], 1);
+            tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_free[s], 128); tc::mbar_init(&p_ready[s], 128); tc::mbar_init(&pv_done[s], 1);
         }
+        for (int s = 0; s < ATTN_RING; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1); }
         tc::fence_barrier_init();
     }
     if (warp == 2) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
 #ifdef SNB_ATTN_TRACE
     if (trace_on && warp == 0) g_attn_trace[5 * 128 + 1] = clock64();
 #endif
 
     if (warp < 4) {
-        setmaxnreg_dec<64>();
+        setmaxnreg_dec<88>();
         if (warp == 0 && lane == 0) {
             // ===================== TMA producer =====================
             const int cq = head * HD, ck = 512 + head * HD, cv = 1024 + head * HD;
@@ -352,17 +114,20 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
                 tc::tma_load_3d(sQ + t * TILE_BYTES, &tmQKV, &q_full[t], cq, q0 + t * BQ, env);
                 tc::tma_load_3d(sQ + t * TILE_BYTES + TILE_BYTES / 2, &tmQKV, &q_full[t], cq + 64, q0 + t * BQ, env);
             }
+            int c = 0;                                   // running index into the K0, K1, V0, K2, V1, ... sequence
+            auto load = [&](int col, int j) {
+                const int slot = c % ATTN_RING;
+                const uint32_t ph = (c / ATTN_RING) & 1;
+                ++c;
+                tc::mbar_wait(&kv_empty[slot], ph ^ 1);
+                tc::mbar_arrive_expect_tx(&kv_full[slot], TILE_BYTES);
+                tc::tma_load_3d(sKV + slot * TILE_BYTES, &tmQKV, &kv_full[slot], col, j * BKV, env);
+                tc::tma_load_3d(sKV + slot * TILE_BYTES + TILE_BYTES / 2, &tmQKV, &kv_full[slot], col + 64, j * BKV, env);
+            };
+            load(ck, 0);
             for (int j = 0; j < n_kv; ++j) {
-                const int st = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                tc::mbar_wait(&k_empty[st], ph ^ 1);
-                tc::mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
-                tc::tma_load_3d(sK + st * TILE_BYTES, &tmQKV, &k_full[st], ck, j * BKV, env);
-                tc::tma_load_3d(sK + st * TILE_BYTES + TILE_BYTES / 2, &tmQKV, &k_full[st], ck + 64, j * BKV, env);
-                tc::mbar_wait(&v_empty[st], ph ^ 1);
-                tc::mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
-                tc::tma_load_3d(sV + st * TILE_BYTES, &tmQKV, &v_full[st], cv, j * BKV, env);
-                tc::tma_load_3d(sV + st * TILE_BYTES + TILE_BYTES / 2, &tmQKV, &v_full[st], cv + 64, j * BKV, env);
+                if (j + 1 < n_kv) load(ck, j + 1);
+                load(cv, j);
             }
         } else if (warp == 1) {
           // ===================== MMA issuer =====================
@@ -370,21 +135,23 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
           // warp-uniform, so the tcgen05.mma operands live in uniform registers instead of being converted per instruction
           const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
           if (tc::elect_one()) {
-            auto kv_cols = [&](int j) { // keys of block j rounded up to the UMMA N granularity (16)
+            auto kv_cols = [&](int j) { // keys of block j rounded up to the UMMA K / N granularity (16)
                 const int rem = n_tok - j * BKV;
                 return rem >= BKV ? BKV : ((rem + 15) & ~15);
             };
             // Issue cost matters (tools/mma_bench*.cu): building a shared-memory descriptor per tcgen05.mma costs ~130 clk per
             // instruction on the issuing thread, twice the 64 clk a 128x128x16 MMA runs.  All descriptors are therefore built
             // once; inside the unrolled K loops an MMA's operands are `base + compile-time constant`.
-            const uint64_t qd0 = tc::make_smem_desc_sw128(tc::smem_u32(sQ), 16, 1024), qd1 = tc::make_smem_desc_sw128(tc::smem_u32(sQ + TILE_BYTES), 16, 1024);
-            const uint64_t kd0 = tc::make_smem_desc_sw128(tc::smem_u32(sK), 16, 1024), kd1 = tc::make_smem_desc_sw128(tc::smem_u32(sK + TILE_BYTES), 16, 1024);
+            const uint64_t qd0 = tc::make_smem_desc_sw128(tc::smem_u32(sQ), 16, 1024);
+            const uint64_t pd0 = tc::make_smem_desc_sw128(tc::smem_u32(sP), 16, 1024);
+            const uint64_t kd0 = tc::make_smem_desc_sw128(tc::smem_u32(sKV), 16, 1024);                 // K: K-major B operand
             // V is the MN-major B operand: 16 keys = 2 groups of 8 rows (SBO 1024 B); the two 64-wide head-dim boxes are LBO = 16 KB apart
-            const uint64_t vd0 = tc::make_smem_desc_sw128(tc::smem_u32(sV), TILE_BYTES / 2, 1024), vd1 = tc::make_smem_desc_sw128(tc::smem_u32(sV + TILE_BYTES), TILE_BYTES / 2, 1024);
-            auto issue_S = [&](int t, int j) {   // caller has waited for Q_t and K(j)
-                const uint64_t qd = t ? qd1 : qd0, kd = (j & 1) ? kd1 : kd0;
+            const uint64_t vd0 = tc::make_smem_desc_sw128(tc::smem_u32(sKV), TILE_BYTES / 2, 1024);
+            constexpr uint64_t TILE_DESC = TILE_BYTES >> 4;  // descriptor start-address units are 16 bytes
+            auto issue_S = [&](int t, int slot, int j) {    // caller has waited for Q_t, K(j) and for S_t to be free
+                const uint64_t qd = qd0 + (uint64_t)t * TILE_DESC, kd = kd0 + (uint64_t)slot * TILE_DESC;
                 const uint32_t idesc = tc::make_idesc_bf16(BQ, (uint32_t)kv_cols(j), 0, 0);
-                const uint32_t d = tmem_base + TM2_S + t * 128;
+                const uint32_t d = tmem_base + TM_S + t * 128;
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k) {
                     const uint64_t off = (uint64_t)(((k >> 2) * (TILE_BYTES / 2) + (k & 3) * 32) >> 4);
@@ -392,133 +159,138 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
                 }
                 tc::umma_commit(&s_full[t]);
             };
-            constexpr uint32_t idesc_pv = tc::make_idesc_bf16(BQ, HD, 0, 1); // B = V is MN-major (head dim contiguous)
-            auto issue_PV = [&](int t, int j) {  // caller has waited for P_t(j) and V(j)
-                const uint64_t vd = (j & 1) ? vd1 : vd0;
-                const uint32_t p_tmem = tmem_base + TM2_S + t * 128;
-                const uint32_t o_tmem = tmem_base + TM2_O + t * 128;
+            constexpr uint32_t idesc_pv = tc::make_idesc_bf16(BQ, HD, 0, 1); // A = P K-major, B = V MN-major (head dim contiguous)
+            auto issue_PV = [&](int t, int slot, int j) {   // caller has waited for P_t(j) and V(j)
+                const uint64_t pd = pd0 + (uint64_t)t * TILE_DESC, vd = vd0 + (uint64_t)slot * TILE_DESC;
+                const uint32_t o_tmem = tmem_base + TM_O + t * 128;
                 const int ksteps = kv_cols(j) / 16;
                 if (ksteps == BKV / 16) {
 #pragma unroll
                     for (int k = 0; k < BKV / 16; ++k)
-                        tc::umma_ts(o_tmem, p_tmem + k * 8, vd + (uint64_t)((k * 2048) >> 4), idesc_pv, (j | k) != 0 ? 1u : 0u);
+                        tc::umma_ss(o_tmem, pd + (uint64_t)(((k >> 2) * (TILE_BYTES / 2) + (k & 3) * 32) >> 4), vd + (uint64_t)((k * 2048) >> 4),
+                                    idesc_pv, (j | k) != 0 ? 1u : 0u);
                 } else {
                     for (int k = 0; k < ksteps; ++k)
-                        tc::umma_ts(o_tmem, p_tmem + k * 8, vd + (uint64_t)((k * 2048) >> 4), idesc_pv, (j | k) != 0 ? 1u : 0u);
+                        tc::umma_ss(o_tmem, pd + (uint64_t)(((k >> 2) * (TILE_BYTES / 2) + (k & 3) * 32) >> 4), vd + (uint64_t)((k * 2048) >> 4),
+                                    idesc_pv, (j | k) != 0 ? 1u : 0u);
                 }
                 tc::umma_commit(&pv_done[t]);
             };
+            int c = 0;                                   // same K0, K1, V0, K2, V1, ... sequence as the producer
+            int slot;
+            auto next_tile = [&]() {
+                slot = c % ATTN_RING;
+                const uint32_t ph = (c / ATTN_RING) & 1;
+                ++c;
+                tc::mbar_wait(&kv_full[slot], ph);
+            };
             tc::mbar_wait(&q_full[0], 0);
-            tc::mbar_wait(&k_full[0], 0);
+            next_tile();                                 // K0
             tc::tc_fence_after();
-            issue_S(0, 0);
+            issue_S(0, slot, 0);
             if (has_b) {
                 tc::mbar_wait(&q_full[1], 0);
                 tc::tc_fence_after();
-                issue_S(1, 0);
+                issue_S(1, slot, 0);
             }
-            tc::umma_commit(&k_empty[0]);
+            tc::umma_commit(&kv_empty[slot]);
             for (int j = 0; j < n_kv; ++j) {
-                const int st = j & 1;
-                const uint32_t ph = j & 1, ring_ph = (j >> 1) & 1;
-                const bool more = j + 1 < n_kv;
-                tc::mbar_wait(&p_ready[0], ph);
-                ATTN_TRACE(4, j, 0);
-                tc::mbar_wait(&v_full[st], ring_ph);
-                tc::tc_fence_after();
-                ATTN_TRACE(4, j, 1);
-                issue_PV(0, j);
-                if (more) {
-                    tc::mbar_wait(&k_full[st ^ 1], ((j + 1) >> 1) & 1);
+                const uint32_t ph = j & 1;
+                if (j + 1 < n_kv) {                      // S(j+1) of both tiles as soon as the softmax warps hold S(j) in registers
+                    next_tile();                         // K(j+1)
+                    tc::mbar_wait(&s_free[0], ph);
                     tc::tc_fence_after();
-                    issue_S(0, j + 1);
+                    ATTN_TRACE(4, j, 0);
+                    issue_S(0, slot, j + 1);
+                    ATTN_TRACE(4, j, 1);
+                    if (has_b) {
+                        tc::mbar_wait(&s_free[1], ph);
+                        tc::tc_fence_after();
+                        issue_S(1, slot, j + 1);
+                    }
+                    ATTN_TRACE(4, j, 2);
+                    tc::umma_commit(&kv_empty[slot]);
                 }
-                ATTN_TRACE(4, j, 2);
+                next_tile();                             // V(j)
+                tc::mbar_wait(&p_ready[0], ph);
+                tc::tc_fence_after();
+                ATTN_TRACE(4, j, 3);
+                issue_PV(0, slot, j);
+                ATTN_TRACE(4, j, 4);
                 if (has_b) {
                     tc::mbar_wait(&p_ready[1], ph);
                     tc::tc_fence_after();
-                    ATTN_TRACE(4, j, 3);
-                    issue_PV(1, j);
-                    if (more) issue_S(1, j + 1);
-                    ATTN_TRACE(4, j, 4);
+                    ATTN_TRACE(4, j, 5);
+                    issue_PV(1, slot, j);
+                    ATTN_TRACE(4, j, 6);
                 }
-                tc::umma_commit(&v_empty[st]);
-                if (more) tc::umma_commit(&k_empty[st ^ 1]);
+                tc::umma_commit(&kv_empty[slot]);
             }
           }
         }
     } else {
-        setmaxnreg_inc<104>();
-        // ===================== softmax / correction / epilogue: tile t, column half `half` of each key block =====================
-        const int t = (warp - 4) >> 3;
-        const int half = ((warp - 4) >> 2) & 1;
+        setmaxnreg_inc<208>();
+        // ===================== softmax / correction / epilogue of tile t =====================
+        const int t = (warp - 4) >> 2;
         if (t == 0 || has_b) {
+            const uint32_t tmem_base = *tmem_slot;
             const int quarter = warp & 3;
             const int row_in_tile = quarter * 32 + lane;
             const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
-            const uint32_t s_addr = tmem_base + lane_addr + TM2_S + t * 128 + half * 64;   // fp32 scores of my 64 keys
-            const uint32_t p_addr = tmem_base + lane_addr + TM2_S + t * 128 + half * 32;   // bf16 pairs of my 64 keys
-            const uint32_t o_addr = tmem_base + lane_addr + TM2_O + t * 128 + half * 64;   // my 64 head-dim columns of O
-            const int pair_bar = 1 + t * 4 + quarter;                                      // named barrier of warps w, w+4
-            float *x_mine = xch + (t * 2 + half) * 128 + row_in_tile;
-            float *x_peer = xch + (t * 2 + (half ^ 1)) * 128 + row_in_tile;
+            const uint32_t s_addr = tmem_base + lane_addr + TM_S + t * 128;
+            const uint32_t o_addr = tmem_base + lane_addr + TM_O + t * 128;
+            // my row of P: 128-byte rows inside 1024-byte 8-row atoms, 16-byte chunk index XORed with (row & 7) (SWIZZLE_128B)
+            uint8_t *p_row = sP + t * TILE_BYTES + row_in_tile * 128;
+            const int sw = row_in_tile & 7;
             const float c = args.scale_log2;
             float m_used = -INFINITY; // running max the exponents are taken against (raw score units)
-            float l = 0.0f;           // partial row sum over my key columns
+            float l = 0.0f;
             for (int j = 0; j < n_kv; ++j) {
                 const uint32_t ph = j & 1;
-                ATTN_TRACE(t * 2 + half, j, 0);
+                ATTN_TRACE(t, j, 0);
                 tc::mbar_wait(&s_full[t], ph);
-                ATTN_TRACE(t * 2 + half, j, 1);
+                ATTN_TRACE(t, j, 1);
                 __syncwarp();                 // reconverge before the .sync.aligned TMEM loads
                 tc::tc_fence_after();
-#if defined(SNB_ATTN_TRACE) && SNB_ATTN_TRACE >= 2   // debug: no softmax work at all -> MMA durations without any contention
-                tc::tc_fence_before();
-                tc::mbar_arrive(&p_ready[t]);
-                continue;
-#endif
-                uint32_t s0[16], s1[16], s2[16], s3[16];   // x16 loads: 16-register operand groups are easier to place than x32
-                tc::tmem_ld_32x16(s_addr, s0);
-                tc::tmem_ld_32x16(s_addr + 16, s1);
-                tc::tmem_ld_32x16(s_addr + 32, s2);
-                tc::tmem_ld_32x16(s_addr + 48, s3);
+                // the whole S row: four 32-column loads in flight, ONE tcgen05.wait::ld
+                uint32_t s0[32], s1[32], s2[32], s3[32];
+                tc::tmem_ld_32x32(s_addr, s0);
+                tc::tmem_ld_32x32(s_addr + 32, s1);
+                tc::tmem_ld_32x32(s_addr + 64, s2);
+                tc::tmem_ld_32x32(s_addr + 96, s3);
                 tc::tmem_ld_wait();
-                ATTN_TRACE(t * 2 + half, j, 2);
-                const int valid = n_tok - j * BKV - half * 64; // keys of my half block that exist
-                if (valid < 64) {                              // ragged last block: keys that do not exist score -inf
+                tc::tc_fence_before();
+                tc::mbar_arrive(&s_free[t]);  // S_t may be overwritten by the next block's Q K^T
+                ATTN_TRACE(t, j, 2);
+                const int valid = n_tok - j * BKV; // keys of this block that exist
+                if (valid < BKV) {                 // ragged last block: keys that do not exist score -inf
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
+                    for (int i = 0; i < 32; ++i) {
                         if (i >= valid) s0[i] = 0xff800000u;
-                        if (16 + i >= valid) s1[i] = 0xff800000u;
-                        if (32 + i >= valid) s2[i] = 0xff800000u;
-                        if (48 + i >= valid) s3[i] = 0xff800000u;
+                        if (32 + i >= valid) s1[i] = 0xff800000u;
+                        if (64 + i >= valid) s2[i] = 0xff800000u;
+                        if (96 + i >= valid) s3[i] = 0xff800000u;
                     }
                 }
-                float mx0 = -INFINITY, mx1 = -INFINITY;
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
-                    mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s2[i]), __uint_as_float(s3[i])));
+                for (int i = 0; i < 32; ++i) {
+                    mx0 = fmaxf(mx0, __uint_as_float(s0[i])); mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
+                    mx2 = fmaxf(mx2, __uint_as_float(s2[i])); mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
                 }
-                // block max of the whole row: exchange with the thread that owns the other 64 keys.  Slots alternate with j,
-                // so slot (j & 1) is rewritten only after the pair barrier of block j+1, which the peer passes after this read.
-                // The barrier also orders the peer's S loads before my P stores (P of keys 64-127 overlays S columns 32-63).
-                x_mine[ph * 512] = fmaxf(mx0, mx1);
-                tc::named_bar_sync(pair_bar, 64);
-                const float bmax = fmaxf(fmaxf(mx0, mx1), x_peer[ph * 512]);
-                ATTN_TRACE(t * 2 + half, j, 3);
+                const float bmax = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
                 if (j == 0) {
                     m_used = bmax;
                 } else if (__any_sync(0xffffffffu, (bmax - m_used) * c > RESCALE_THRESHOLD)) {
-                    // Refresh the running max.  The decision is uniform over the warp (tcgen05.ld/st are .sync.aligned) and
-                    // identical in the peer warp (same rows, same bmax); lanes whose own max did not grow rescale by exactly 1.
-                    tc::mbar_wait(&pv_done[t], (j - 1) & 1);              // O is stable once the previous PV has landed
+                    // Refresh the running max.  The decision is WARP-uniform (tcgen05.ld/st are .sync.aligned and must be
+                    // executed by all 32 lanes together); lanes whose own max did not grow rescale by exactly 1.
+                    tc::mbar_wait(&pv_done[t], (j - 1) & 1);              // O_t is stable once PV_t(j-1) has landed
                     __syncwarp();
                     tc::tc_fence_after();
                     const float m_new = fmaxf(m_used, bmax);
                     const float f = tc::ex2_approx((m_used - m_new) * c);
 #pragma unroll 1
-                    for (int ch = 0; ch < 4; ++ch) {
+                    for (int ch = 0; ch < 8; ++ch) {
                         uint32_t r[16];
                         tc::tmem_ld_32x16(o_addr + ch * 16, r);
                         tc::tmem_ld_wait();
@@ -526,49 +298,72 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
                         for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
                         tc::tmem_st_32x16(o_addr + ch * 16, r);
                     }
+                    tc::tmem_st_wait();
+                    tc::tc_fence_before();
                     l *= f;
                     m_used = m_new;
                 }
                 const float mc = m_used * c;
-                float sum0 = 0.0f, sum1 = 0.0f;
-                auto exp_pack = [&](const uint32_t (&sa)[16], const uint32_t (&sb)[16], uint32_t col) {
-                    uint32_t pk[16];
+                // exponentials first, into registers (packed bf16 pairs overwrite the scores they came from): pairs of keys on
+                // FFMA2 / FADD2; one pair in POLY_EVERY takes the FMA-pipe polynomial instead of MUFU.EX2
+                const uint64_t c2 = tc::f2_pack(c, c), nmc2 = tc::f2_pack(-mc, -mc);
+                uint64_t sumA = tc::f2_pack(0.0f, 0.0f), sumB = sumA;
+                auto exp_pack = [&](uint32_t (&s)[32]) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float a0 = tc::ex2_approx(fmaf(__uint_as_float(sa[2 * i]), c, -mc)), a1 = tc::ex2_approx(fmaf(__uint_as_float(sa[2 * i + 1]), c, -mc));
-                        const float b0 = tc::ex2_approx(fmaf(__uint_as_float(sb[2 * i]), c, -mc)), b1 = tc::ex2_approx(fmaf(__uint_as_float(sb[2 * i + 1]), c, -mc));
-                        sum0 += a0 + a1; sum1 += b0 + b1;
-                        pk[i] = tc::pack_bf16(a0, a1); pk[8 + i] = tc::pack_bf16(b0, b1);
+                    for (int i = 0; i < 16; ++i) {
+                        const uint64_t x2 = tc::f2_fma(tc::f2_pack(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), c2, nmc2);
+                        uint64_t e2;
+                        if (POLY_EVERY > 0 && (i % POLY_EVERY) == POLY_EVERY - 1) {
+                            e2 = tc::f2_exp2_poly(x2);
+                        } else {
+                            float xl, xh;
+                            tc::f2_unpack(x2, xl, xh);
+                            e2 = tc::f2_pack(tc::ex2_approx(xl), tc::ex2_approx(xh));
+                        }
+                        if (i & 1) sumB = tc::f2_add(sumB, e2); else sumA = tc::f2_add(sumA, e2);
+                        float el, eh;
+                        tc::f2_unpack(e2, el, eh);
+                        s[i] = tc::pack_bf16(el, eh);
                     }
-                    tc::tmem_st_32x16(p_addr + col, pk);
                 };
-                exp_pack(s0, s1, 0);       // P columns [0,16) of my half  <- S columns [0,32)
-                exp_pack(s2, s3, 16);      // P columns [16,32) of my half <- S columns [32,64)
-                l += sum0 + sum1;
-                ATTN_TRACE(t * 2 + half, j, 4);
-                tc::tmem_st_wait();
-                tc::tc_fence_before();
+                exp_pack(s0); exp_pack(s1); exp_pack(s2); exp_pack(s3);
+                {
+                    float a0, a1, b0, b1;
+                    tc::f2_unpack(sumA, a0, a1);
+                    tc::f2_unpack(sumB, b0, b1);
+                    l += (a0 + a1) + (b0 + b1);
+                }
+                ATTN_TRACE(t, j, 3);
+                // ... then the P row goes to shared memory once PV_t(j-1) has consumed the previous one (normally long ago)
+                if (j > 0) tc::mbar_wait(&pv_done[t], (j - 1) & 1);
+                auto store = [&](const uint32_t (&s)[32], int box, int chunk0) {   // 32 keys = four 16-byte chunks of my P row
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<uint4 *>(p_row + box * (TILE_BYTES / 2) + (((chunk0 + q) ^ sw) << 4)) =
+                            make_uint4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
+                };
+                store(s0, 0, 0); store(s1, 0, 4); store(s2, 1, 0); store(s3, 1, 4);
+                ATTN_TRACE(t, j, 4);
+                tc::fence_proxy_async();      // generic-proxy stores -> visible to the tensor core's async-proxy reads
                 tc::mbar_arrive(&p_ready[t]);
-                ATTN_TRACE(t * 2 + half, j, 5);
+                ATTN_TRACE(t, j, 5);
             }
-            // final: O / l -> global (l = my partial sum + the peer's)
-            x_mine[(n_kv & 1) * 512] = l;
-            tc::named_bar_sync(pair_bar, 64);
-            const float inv_l = 1.0f / (l + x_peer[(n_kv & 1) * 512]);
+            // final: O / l -> global
             tc::mbar_wait(&pv_done[t], (n_kv - 1) & 1);
             __syncwarp();
             tc::tc_fence_after();
+            const float inv_l = 1.0f / l;
             const int row = q0 + t * BQ + row_in_tile;
-            bf16 *dst = args.out + ((size_t)env * n_tok + row) * (NHEAD * HD) + head * HD + half * 64;
+            bf16 *dst = args.out + ((size_t)env * n_tok + row) * (NHEAD * HD) + head * HD;
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
-                uint32_t r[16];
-                tc::tmem_ld_32x16(o_addr + ch * 16, r);
+                uint32_t r[32];
+                tc::tmem_ld_32x32(o_addr + ch * 32, r);
                 tc::tmem_ld_wait();
                 if (row < n_tok) {
-                    uint4 *o4 = reinterpret_cast<uint4 *>(dst + ch * 16);
+                    uint4 *o4 = reinterpret_cast<uint4 *>(dst + ch * 32);
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
+                    for (int q = 0; q < 4; ++q) {
                         uint4 o;
                         o.x = tc::pack_bf16(__uint_as_float(r[8 * q + 0]) * inv_l, __uint_as_float(r[8 * q + 1]) * inv_l);
                         o.y = tc::pack_bf16(__uint_as_float(r[8 * q + 2]) * inv_l, __uint_as_float(r[8 * q + 3]) * inv_l);
@@ -588,7 +383,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
         g_attn_trace[5 * 128 + 2] = clock64(); g_attn_trace[5 * 128 + 4] = gt;
     }
 #endif
-    if (warp == 2) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (warp == 2) tc::tmem_dealloc<TMEM_COLS>(__shfl_sync(0xffffffffu, *tmem_slot, 0));
 }
 
 // iMID: R independent sequences of T <= 32 tokens (TransformerConcatLinear, diffusion.py:147).  One warp per
@@ -646,24 +441,13 @@ int snb_attn_launch(const AttnPlan *plan, bf16 *out, cudaStream_t stream)
 {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    static bool use_v1 = false;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
-        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN2_SMEM);
-        const char *e = getenv("SNB_ATTN_V1");
-        use_v1 = e && e[0] == '1';
-    });
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM); });
     SNB_CUDA_TRY(attr_err);
     AttnArgs a;
     a.out = out; a.n_tok = plan->n_tok;
     a.scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
-    if (use_v1) {
-        dim3 grid((plan->n_tok + BQ - 1) / BQ, NHEAD, plan->n_env);
-        attn_fwd_kernel<<<grid, ATTN_THREADS, ATTN_SMEM, stream>>>(plan->tmQKV, a);
-    } else {
-        dim3 grid((plan->n_tok + 2 * BQ - 1) / (2 * BQ), NHEAD, plan->n_env);
-        attn_fwd2_kernel<<<grid, ATTN2_THREADS, ATTN2_SMEM, stream>>>(plan->tmQKV, a);
-    }
+    dim3 grid((plan->n_tok + 2 * BQ - 1) / (2 * BQ), NHEAD, plan->n_env);
+    attn_fwd_kernel<<<grid, ATTN_THREADS, ATTN_SMEM, stream>>>(plan->tmQKV, a);
     snb_count_launch();
     SNB_CUDA_TRY(cudaGetLastError());
     return SNB_OK;

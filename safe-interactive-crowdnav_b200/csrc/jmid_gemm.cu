@@ -138,7 +138,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * Cfg::STAGES + 4);
     float *s_bias = reinterpret_cast<float *>(smem + Cfg::OFF_BIAS);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int m_tiles = (M + BM - 1) / BM, n_tiles = N / BN;
     const int num_tiles = m_tiles * n_tiles;
     const int k_blocks = K / BK;
@@ -176,8 +176,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // Issue cost (tools/mma_bench*.cu): a descriptor built per tcgen05.mma from per-thread registers costs ~130 clk on the
+        // issuing thread.  The warp index and the TMEM base are made provably warp-uniform (shuffle broadcasts), one elected
+        // thread issues, and inside the unrolled K loop an MMA's descriptors are `stage base + compile-time constant`.
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        if (tc::elect_one()) {
             constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN, 0, 0);
+            const uint64_t da0 = tc::make_smem_desc_sw128(tc::smem_u32(smem), 16, 1024);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -186,18 +191,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint32_t acc_phase = (it >> 1) & 1;
                 tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tmem_u + acc * BN;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     tc::mbar_wait(&full[stage], phase);
                     tc::tc_fence_after();
-                    const uint32_t a_addr = tc::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+                    const uint64_t da = da0 + (uint64_t)stage * (Cfg::STAGE_BYTES >> 4), db = da + (Cfg::A_BYTES >> 4);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t da = tc::make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-                        const uint64_t db = tc::make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                        tc::umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-                    }
+                    for (int k = 0; k < BK / 16; ++k)
+                        tc::umma_ss(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
                     tc::umma_commit(&empty[stage]);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -276,7 +277,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * Cfg::STAGES + 4);
     float *s_bias = reinterpret_cast<float *>(smem + Cfg::OFF_BIAS);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const uint32_t rank = tc::cluster_ctarank();
     const bool leader = rank == 0;
     const int m_tiles = (M + 2 * BM - 1) / (2 * BM), n_tiles = N / BN;
@@ -319,8 +320,11 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
-        if (leader && lane == 0) {
+        // (issue cost: see the single-CTA kernel -- uniform warp index / TMEM base, one elected thread, precomputed descriptors)
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        if (leader && tc::elect_one()) {
             constexpr uint32_t idesc = tc::make_idesc_bf16(2 * BM, BN, 0, 0);
+            const uint64_t da0 = tc::make_smem_desc_sw128(tc::smem_u32(smem), 16, 1024);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -329,18 +333,14 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const uint32_t acc_phase = (it >> 1) & 1;
                 tc::mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tmem_u + acc * BN;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     tc::mbar_wait(&full[stage], phase);
                     tc::tc_fence_after();
-                    const uint32_t a_addr = tc::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+                    const uint64_t da = da0 + (uint64_t)stage * (Cfg::STAGE_BYTES >> 4), db = da + (Cfg::A_BYTES >> 4);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t da = tc::make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-                        const uint64_t db = tc::make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                        tc::umma_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-                    }
+                    for (int k = 0; k < BK / 16; ++k)
+                        tc::umma_ss_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
                     tc::umma_commit_pair(&empty[stage]);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }

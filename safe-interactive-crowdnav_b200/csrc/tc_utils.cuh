@@ -256,4 +256,47 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
     return *reinterpret_cast<uint32_t *>(&v);
 }
 
+// ------------------------------------------------------------------ packed fp32 pairs (sm_100: FFMA2 / FADD2, one issue slot for two lanes)
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi)
+{
+    uint64_t v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b)
+{
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// 2^x for a pair on the FMA pipe instead of the SFU (the softmax of a 128x128 score block needs 16384 exponentials: at
+// 16 MUFU.EX2 / clk / SM that is as long as the block's two MMAs, so a fraction is computed here).  Cody-Waite split
+// x = n + r, n = round(x), |r| <= 0.5; 2^r by a degree-3 minimax polynomial (max relative error 1.0e-4, far below the bf16
+// rounding of P); 2^n by adding n to the exponent field.  Valid for -126 <= x < 128; smaller x are clamped (result ~1e-38).
+__device__ __forceinline__ uint64_t f2_exp2_poly(uint64_t x2)
+{
+    float xl, xh;
+    f2_unpack(x2, xl, xh);
+    const uint64_t xc = f2_pack(fmaxf(xl, -126.0f), fmaxf(xh, -126.0f));
+    const uint64_t magic = f2_pack(12582912.0f, 12582912.0f), neg_magic = f2_pack(-12582912.0f, -12582912.0f);
+    const uint64_t xf = f2_add(xc, magic);                       // low mantissa bits = round(x)
+    const uint64_t n = f2_add(xf, neg_magic);
+    const uint64_t r = f2_fma(n, f2_pack(-1.0f, -1.0f), xc);
+    uint64_t p = f2_fma(f2_pack(0.05500893f, 0.05500893f), r, f2_pack(0.24221095f, 0.24221095f));
+    p = f2_fma(p, r, f2_pack(0.6932829f, 0.6932829f));
+    p = f2_fma(p, r, f2_pack(1.0f, 1.0f));
+    float pl, ph, fl, fh;
+    f2_unpack(p, pl, ph);
+    f2_unpack(xf, fl, fh);
+    return f2_pack(__int_as_float(__float_as_int(pl) + (__float_as_int(fl) << 23)), __int_as_float(__float_as_int(ph) + (__float_as_int(fh) << 23)));
+}
+
 } // namespace tc

@@ -24,9 +24,9 @@ cta = tr[5, 0]
 tr = tr[:5]
 t0 = cta[0]
 print(f"CTA: setup done +{cta[1]-t0}, end +{cta[2]-t0} clk; {cta[4]-cta[3]} ns -> {(cta[2]-t0)/(cta[4]-cta[3])*1e3:.0f} MHz")
-names = ["A.h0", "A.h1", "B.h0", "B.h1", "MMA"]
-print("softmax events: 0 wait-start 1 s_full 2 ld-done 3 max-exchanged 4 exps-done 5 arrived;  MMA: 0 pA 1 vfull 2 issuedA 3 pB 4 issuedB 5 PV_A issued 6 PV_A done 7 S_A done")
+names = ["A", "B", "-", "-", "MMA"]
+print("softmax: 0 wait-start 1 s_full 2 S loaded+released 3 pv_done(j-1) seen 4 exps+P stored 5 arrived;  MMA: 0 K(j+1)+s_free[A] 1 S_A issued 2 S_B issued 3 p_ready[A] 4 PV_A issued 5 p_ready[B] 6 PV_B issued")
 for j in range(13):
-    for r in range(5):
+    for r in (0, 1, 4):
         ev = tr[r, j]
         print(f"j={j:2d} {names[r]:5s} " + " ".join(f"{(int(e) - t0) if e > 0 else -1:7d}" for e in ev[:8]))
