@@ -111,6 +111,26 @@ int32_t snb_obstacles_num_vertices(const SnbObstacles *obs);
 int snb_obstacles_get_vertex(const SnbObstacles *obs, int32_t i, float *out7_host);
 
 /*
+ * Batched seeded scenario reset (CrowdSimPlus.reset -> generate_random_human_position, crowd_sim_plus.py:609-764, 425-451;
+ * generate_circle_crossing_human :454-481; generate_hallway_human :522-605; Human.get_g_xy human_plus.py:19-52).
+ * One thread per environment consumes the PCG64 stream of numpy's default_rng(seeds[b]) (SeedSequence hashing included) in the
+ * reference's draw order and writes every human array of `state`, the robot at (0,-R) -> (0,R), rtheta = pi/2, clocks 0.
+ * rule: SNB_SCENE_CIRCLE_CROSSING, or SNB_SCENE_HALLWAY for every rule generate_hallway_human serves (hallway,
+ * hallway_static[_with_back], hallway_bottleneck, hallway_squeeze, rectangle, left_wall, no_walls; the segment list and the
+ * door configuration carry the difference).  seeds_dev [B] uint64 = case offset + test case (:658-664).
+ * segs_dev [n_seg*4] x1,y1,x2,y2 on the device.  n_draws_dev (optional int32 [B]) receives the number of 64-bit draws used,
+ * or -1 where the rejection sampling gave up after 200 000 tries (an over-crowded scene; the reference would spin forever).
+ */
+#define SNB_SCENE_CIRCLE_CROSSING 0
+#define SNB_SCENE_HALLWAY 1
+typedef struct SnbSceneCfg {
+    int32_t rule, randomize_attributes;
+    double circle_radius, rect_width, rect_height, human_radius, human_v_pref, robot_radius, discomfort_dist;
+} SnbSceneCfg;
+int snb_scene_reset(const SnbSceneCfg *cfg, const SnbDoorCfg *door /* may be NULL */, const SnbCrowdState *state,
+                    const uint64_t *seeds_dev, const double *segs_dev, int32_t n_seg, int32_t *n_draws_dev, void *stream);
+
+/*
  * Human policy for every human of every environment, no clamp / integration:
  *   ORCA.predict (orca.py:82-133), ORCAPlus.predict (orca_plus.py:29-90), SFM.predict (social_force.py:38-94)
  * batched over B*H agents.  out_v_dev [B*H*2] (vx,vy).  Optional (ORCA only): nbr_dev [B*H*max_neighbors]
@@ -132,6 +152,21 @@ int snb_env_step(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const SnbRewar
                  const SnbCrowdState *state, const SnbObstacles *obs, const double *robot_action_dev,
                  const uint8_t *active_dev, double *reward_dev, double *dmin_dev, int32_t *flags_dev,
                  int32_t *nbr_dev, int32_t *nbr_cnt_dev, int32_t *status_dev, void *stream);
+
+/*
+ * CrowdSimPlus.step(action, update=False) -- the one-step look-ahead the RL observation builders call once per
+ * discrete action (crowd_sim_plus.py:797-866 -> step(update=False), :1239-1255) -- for n_actions candidate robot
+ * actions per environment in ONE launch.  The humans react to the current state only, so their policy (ORCA / SFM)
+ * and clamp run once per environment; every candidate action then gets its own robot clamp, collision scan and
+ * reward.  Nothing in `state` is modified (prev_dist included, crowd_sim_plus.py:1136-1137).
+ *   robot_actions_dev [B, n_actions, 2];  outputs (each optional) reward_dev / dmin_dev / flags_dev [B, n_actions],
+ *   next_humans_dev [B, H, 4] = Agent.get_next_observable_state (agent_plus.py:86-98) px,py,vx,vy of every human,
+ *   next_robot_dev [B, n_actions, 2] = the robot's constrained next position.
+ */
+int snb_env_whatif(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const SnbRewardCfg *reward_cfg,
+                   const SnbCrowdState *state, const SnbObstacles *obs, const double *robot_actions_dev,
+                   int32_t n_actions, const uint8_t *active_dev, double *reward_dev, double *dmin_dev,
+                   int32_t *flags_dev, double *next_humans_dev, double *next_robot_dev, int32_t *status_dev, void *stream);
 
 /*
  * Host-buffer form of one policy call -- the literal replacement of what `policy.predict(state)` does behind

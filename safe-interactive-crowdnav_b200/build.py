@@ -22,6 +22,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-I", os.path.join(ROOT, "include"),
 UNITS = [
     ("snb_api.cu", []),
     ("crowd_kernels.cu", ["-fmad=false", "-Xcompiler", "-ffp-contract=off"]),
+    ("scene_kernels.cu", ["-fmad=false", "-Xcompiler", "-ffp-contract=off"]),
     ("jmid_kernels.cu", []),
     ("jmid_gemm.cu", []),
     ("jmid_attn.cu", []),

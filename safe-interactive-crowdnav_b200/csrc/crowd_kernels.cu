@@ -187,7 +187,10 @@ struct CrowdParams {
     const BspNode *nodes;
     int bsp_root;
     int epc;       // environments per CTA
-    int full_step; // 0 = policy only, 1 = CrowdSimPlus.step
+    int full_step; // 0 = policy only, 1 = CrowdSimPlus.step(update=True), 2 = step(update=False) for n_actions candidate robot actions
+    int n_actions; // full_step == 2: robot_action is [B, n_actions, 2]; reward / dmin / flags are [B, n_actions]
+    double *next_h;     // full_step == 2: [B, H, 4] next observable human states (px, py, vx, vy)
+    double *next_robot; // full_step == 2: [B, n_actions, 2] constrained next robot position (optional)
 };
 
 struct Line { float px, py, dx, dy; };
@@ -1117,13 +1120,17 @@ __global__ void __launch_bounds__(CROWD_THREADS) crowd_step_kernel(const CrowdPa
     }
     __syncthreads();
 
-    // ---- phase 2b: one thread per environment: robot clamp, collision scan, reward, robot update, clocks ----
-    for (int e = tid; e < nenv; e += blockDim.x) {
+    // ---- phase 2b: one thread per (environment, candidate robot action): robot clamp, collision scan, reward;
+    //      update=True (one action): robot update and clocks; update=False: outputs only, the state is not touched ----
+    const int nact = P.full_step == 2 ? P.n_actions : 1;
+    for (int ea = tid; ea < nenv * nact; ea += blockDim.x) {
+        const int e = ea / nact, a = ea - e * nact;
         const int genv = env0 + e;
         if (P.active && !P.active[genv]) continue;
+        const size_t oidx = (size_t)genv * nact + a;
         const double rpx = T.ex_px[e * E], rpy = T.ex_py[e * E], rrad = T.ex_rad[e * E];
         const double rtheta = P.st.rtheta[genv];
-        const double ra0 = P.robot_action[2 * genv], ra1 = P.robot_action[2 * genv + 1];
+        const double ra0 = P.robot_action[2 * oidx], ra1 = P.robot_action[2 * oidx + 1];
         const int kin = P.st.robot_kinematics;
         double c0 = ra0, c1 = ra1;
         if (P.n_seg > 0) constrain_action(rpx, rpy, rtheta, rrad, dt, kin, ra0, ra1, P.n_seg, T.segs, c0, c1);
@@ -1157,12 +1164,16 @@ __global__ void __launch_bounds__(CROWD_THREADS) crowd_step_kernel(const CrowdPa
         }
         if (P.rcfg.has_progress) {
             rew += (P.st.prev_dist[genv] - curr_dist) * P.rcfg.progress_factor;
-            P.st.prev_dist[genv] = curr_dist;
+            if (P.full_step == 1) P.st.prev_dist[genv] = curr_dist;   // crowd_sim_plus.py:1136-1137: only when update
         }
         if (frozen) { rew += P.rcfg.freezing_penalty; f |= SNB_F_FROZEN; }
-        if (P.reward) P.reward[genv] = rew;
-        if (P.dmin) P.dmin[genv] = dmin;
-        if (P.flags) P.flags[genv] = f;
+        if (P.reward) P.reward[oidx] = rew;
+        if (P.dmin) P.dmin[oidx] = dmin;
+        if (P.flags) P.flags[oidx] = f;
+        if (P.full_step == 2) {
+            if (P.next_robot) { P.next_robot[2 * oidx] = rnx; P.next_robot[2 * oidx + 1] = rny; }
+            continue;
+        }
         // Agent.step for the robot (agent_plus.py:199-214)
         const size_t gx = (size_t)genv * E;
         P.st.ex_px[gx] = rnx; P.st.ex_py[gx] = rny;
@@ -1187,12 +1198,17 @@ __global__ void __launch_bounds__(CROWD_THREADS) crowd_step_kernel(const CrowdPa
         const size_t g = goff + task;
         const double c0 = T.act[2 * task], c1 = T.act[2 * task + 1];
         const double nx = s_next[2 * task], ny = s_next[2 * task + 1];
+        if (P.full_step == 2) {   // Agent.get_next_observable_state (agent_plus.py:86-98), holonomic humans
+            if (P.next_h) { P.next_h[4 * g] = nx; P.next_h[4 * g + 1] = ny; P.next_h[4 * g + 2] = c0; P.next_h[4 * g + 3] = c1; }
+            continue;
+        }
         P.st.px[g] = nx; P.st.py[g] = ny; P.st.vx[g] = c0; P.st.vy[g] = c1;
         P.st.theta[g] = atan2(c1, c0);
         double ngx, ngy;
         get_g_xy(P.door, nx, ny, P.st.fgx[g], P.st.fgy[g], ngx, ngy);
         P.st.gx[g] = ngx; P.st.gy[g] = ngy;
     }
+    if (P.full_step == 2) return;
     __syncthreads(); // phase 2b's global_time stores are visible to the CTA after this barrier
     for (int task = tid; task < nA; task += blockDim.x) {
         const int e = task / H;
@@ -1228,7 +1244,8 @@ static size_t crowd_smem_bytes(int epc, int H, int E, int n_seg)
 
 static int launch_crowd(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const SnbRewardCfg *rcfg, const SnbCrowdState *st,
                         const SnbObstacles *obs, const double *robot_action, const uint8_t *active, double *reward,
-                        double *dmin, int *flags, double *out_v, int *nbr, int *nbr_cnt, int *status, int full_step, void *stream)
+                        double *dmin, int *flags, double *out_v, int *nbr, int *nbr_cnt, int *status, int full_step, void *stream,
+                        int n_actions = 1, double *next_h = nullptr, double *next_robot = nullptr)
 {
     SNB_REQUIRE(cfg && st, SNB_EINVAL, "crowd step: cfg/state is NULL");
     SNB_REQUIRE(st->B >= 0 && st->H >= 1 && st->E >= 0, SNB_EINVAL, "crowd step: bad sizes B=%d H=%d E=%d", st->B, st->H, st->E);
@@ -1264,6 +1281,7 @@ static int launch_crowd(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const S
     } else { P.bsp_root = -1; }
     P.epc = choose_epc(st->H);
     P.full_step = full_step;
+    P.n_actions = n_actions; P.next_h = next_h; P.next_robot = next_robot;
 
     const size_t smem = crowd_smem_bytes(P.epc, st->H, st->E, P.n_seg);
     static std::once_flag once;
@@ -1292,6 +1310,16 @@ extern "C" int snb_env_step(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, con
 {
     return launch_crowd(cfg, door, reward_cfg, state, obs, robot_action_dev, active_dev, reward_dev, dmin_dev, flags_dev,
                         nullptr, nbr_dev, nbr_cnt_dev, status_dev, 1, stream);
+}
+
+extern "C" int snb_env_whatif(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const SnbRewardCfg *reward_cfg,
+                              const SnbCrowdState *state, const SnbObstacles *obs, const double *robot_actions_dev,
+                              int32_t n_actions, const uint8_t *active_dev, double *reward_dev, double *dmin_dev,
+                              int32_t *flags_dev, double *next_humans_dev, double *next_robot_dev, int32_t *status_dev, void *stream)
+{
+    SNB_REQUIRE(n_actions >= 1, SNB_EINVAL, "env what-if: n_actions=%d", n_actions);
+    return launch_crowd(cfg, door, reward_cfg, state, obs, robot_actions_dev, active_dev, reward_dev, dmin_dev, flags_dev,
+                        nullptr, nullptr, nullptr, status_dev, 2, stream, n_actions, next_humans_dev, next_robot_dev);
 }
 
 // ---- host-buffer single call: what policy.predict(state) does behind the rvo2 FFI ----

@@ -40,6 +40,14 @@ class DoorCfg(C.Structure):
                 ("door_y_min", _d), ("door_y_max", _d), ("door_width", _d)]
 
 
+class SceneCfg(C.Structure):
+    _fields_ = [("rule", _i32), ("randomize_attributes", _i32), ("circle_radius", _d), ("rect_width", _d), ("rect_height", _d),
+                ("human_radius", _d), ("human_v_pref", _d), ("robot_radius", _d), ("discomfort_dist", _d)]
+
+
+SCENE_CIRCLE_CROSSING, SCENE_HALLWAY = 0, 1
+
+
 class RewardCfg(C.Structure):
     _fields_ = [("success_reward", _d), ("timeout", _d), ("collision_penalty", _d), ("wall_collision_penalty", _d),
                 ("freezing_penalty", _d), ("discomfort", _i32), ("has_progress", _i32), ("discomfort_dist", _d),
@@ -99,6 +107,9 @@ _proto("snb_obstacles_get_vertex", C.c_int, [_vp, _i32, C.POINTER(C.c_float)])
 _proto("snb_policy_step", C.c_int, [C.POINTER(PolicyCfg), C.POINTER(CrowdState), _vp, _vp, _vp, _vp, _vp, _vp])
 _proto("snb_env_step", C.c_int, [C.POINTER(PolicyCfg), C.POINTER(DoorCfg), C.POINTER(RewardCfg), C.POINTER(CrowdState),
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp])
+_proto("snb_scene_reset", C.c_int, [C.POINTER(SceneCfg), C.POINTER(DoorCfg), C.POINTER(CrowdState), _vp, _vp, _i32, _vp, _vp])
+_proto("snb_env_whatif", C.c_int, [C.POINTER(PolicyCfg), C.POINTER(DoorCfg), C.POINTER(RewardCfg), C.POINTER(CrowdState),
+                                    _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp])
 _proto("snb_policy_predict_host", C.c_int, [C.POINTER(PolicyCfg), C.POINTER(_d), _i32, C.POINTER(_d), _i32, C.POINTER(_d),
                                              C.POINTER(_d), C.POINTER(_i32), C.POINTER(_i32)])
 _proto("snb_jmid_create", C.c_int, [C.POINTER(_vp), C.POINTER(JmidWeights), _i32, _i32, _i32, _i32, _i32, _vp], required=False)

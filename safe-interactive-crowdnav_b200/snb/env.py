@@ -102,34 +102,56 @@ class CrowdSimPlusBatch:
                                progress_factor=r.get("progress_factor", 0.0), time_limit=self.time_limit)
 
     # ------------------------------------------------------------------ reset
-    def reset(self, phase='test', test_cases=None):
+    def reset(self, phase='test', test_cases=None, on_device=True):
         """Builds env b from test case `test_cases[b]` (default b) with the reference's seeding
-        (default_rng(offset + case), crowd_sim_plus.py:658-664), uploads the SoA state, runs the `starts_moving`
-        warm-up steps with a zero robot action (:709-720).  Returns the observation dict."""
+        (default_rng(offset + case), crowd_sim_plus.py:658-664), runs the `starts_moving` warm-up steps with a zero robot
+        action (:709-720).  Returns the observation dict.
+        on_device (default): the scenes are generated by snb_scene_reset, one thread per environment consuming the same
+        PCG64 stream; on_device=False runs the host restatement (snb/scenario.py) and uploads -- same draws, same accept /
+        reject decisions, positions equal to the last ulp of cos / sin / atan2.  The debug layout (case -1) is host only."""
         assert phase in ('train', 'val', 'test')
         self.phase = phase
         self.sim_env = self.test_sim if phase == 'test' else self.train_val_sim
         cases = np.arange(self.B) if test_cases is None else np.asarray(test_cases).reshape(self.B)
         p = scenario.SceneParams(self.circle_radius, self.rect_width, self.rect_height, self.human_radius, self.human_v_pref,
                                  self.robot_radius, self.rewards["discomfort_dist"], self.randomize_attributes)
-        H = 3 if (len(cases) and cases[0] == -1) else self.human_num
-        hum = np.zeros((self.B, H, 8))
-        segs = door = None
-        for b, case in enumerate(cases):
-            sc = scenario.generate_scene(self.sim_env, H, int(case), phase, p, {'val': self.case_capacity['val'], 'test': self.case_capacity['test']})
-            hum[b] = sc["humans"]
-            segs, door = sc["segs"], sc["door"]
+        debug_case = bool(len(cases) and cases[0] == -1)
+        H = 3 if debug_case else self.human_num
+        kin = _capi.KIN_HOLONOMIC if self.robot_kinematics == "holonomic" else _capi.KIN_UNICYCLE
+        st = CrowdStateSoA(self.B, H, 1, self.device, kin, self.robot_visible)
+        if self.sim_env != 'circle_crossing' and self.sim_env not in scenario.HALLWAY_RULES:
+            raise ValueError("Rule doesn't exist (square_crossing is broken in the reference, quirk q9)")
+        segs, door = scenario.static_obstacles(self.sim_env, p)
         self._door = door
         self.static_obstacles = [[(s[0], s[1]), (s[2], s[3])] for s in segs]
         self.obstacles = Obstacles(segs) if len(segs) else None
         if self.sim_env == 'hallway_bottleneck' and getattr(self.human_policy, 'name', '') == 'sfm':
             self.human_policy.is_bottleneck = True     # crowd_sim_plus.py:448-449
-        kin = _capi.KIN_HOLONOMIC if self.robot_kinematics == "holonomic" else _capi.KIN_UNICYCLE
-        st = CrowdStateSoA(self.B, H, 1, self.device, kin, self.robot_visible)
-        st.load_numpy(px=hum[:, :, 0], py=hum[:, :, 1], gx=hum[:, :, 2], gy=hum[:, :, 3], fgx=hum[:, :, 4], fgy=hum[:, :, 5],
-                      vpref=hum[:, :, 6], theta=hum[:, :, 7], radius=np.full((self.B, H), self.human_radius))
-        st.ex_px.fill_(0.0); st.ex_py.fill_(-self.circle_radius); st.ex_radius.fill_(self.robot_radius)
-        st.rgx.fill_(0.0); st.rgy.fill_(self.circle_radius); st.rtheta.fill_(np.pi / 2)
+        if on_device and not debug_case:
+            cap = {'val': self.case_capacity['val'], 'test': self.case_capacity['test']}
+            offset = {"train": cap["val"] + cap["test"], "val": 0, "test": cap["val"]}[phase]
+            seeds = torch.from_numpy((cases.astype(np.int64) + offset).astype(np.uint64).view(np.int64)).to(self.device)
+            scfg = _capi.SceneCfg(rule=_capi.SCENE_CIRCLE_CROSSING if self.sim_env == 'circle_crossing' else _capi.SCENE_HALLWAY,
+                                  randomize_attributes=int(self.randomize_attributes), circle_radius=self.circle_radius,
+                                  rect_width=self.rect_width, rect_height=self.rect_height, human_radius=self.human_radius,
+                                  human_v_pref=self.human_v_pref, robot_radius=self.robot_radius, discomfort_dist=self.rewards["discomfort_dist"])
+            segs_dev = torch.from_numpy(np.ascontiguousarray(segs, np.float64).reshape(-1)).to(self.device) if len(segs) else None
+            self.reset_draws = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+            dc = self._door_cfg()
+            cs = st.cstruct()
+            _capi.check(_capi.lib.snb_scene_reset(C.byref(scfg), C.byref(dc), C.byref(cs), _capi.ptr(seeds), _capi.ptr(segs_dev), len(segs),
+                                                  _capi.ptr(self.reset_draws), _capi.stream_ptr()), "snb_scene_reset")
+            if int(self.reset_draws.min().item()) < 0:
+                raise _capi.SnbError("scene reset: rejection sampling gave up (over-crowded scene: too many humans for this layout)")
+        else:
+            hum = np.zeros((self.B, H, 8))
+            for b, case in enumerate(cases):
+                sc = scenario.generate_scene(self.sim_env, H, int(case), phase, p, {'val': self.case_capacity['val'], 'test': self.case_capacity['test']})
+                hum[b] = sc["humans"]
+            st.load_numpy(px=hum[:, :, 0], py=hum[:, :, 1], gx=hum[:, :, 2], gy=hum[:, :, 3], fgx=hum[:, :, 4], fgy=hum[:, :, 5],
+                          vpref=hum[:, :, 6], theta=hum[:, :, 7], radius=np.full((self.B, H), self.human_radius))
+            st.ex_px.fill_(0.0); st.ex_py.fill_(-self.circle_radius); st.ex_radius.fill_(self.robot_radius)
+            st.rgx.fill_(0.0); st.rgy.fill_(self.circle_radius); st.rtheta.fill_(np.pi / 2)
         self.state = st
         self.active = torch.ones(self.B, dtype=torch.uint8, device=self.device)
         self.reward = torch.zeros(self.B, dtype=torch.float64, device=self.device)
@@ -166,6 +188,31 @@ class CrowdSimPlusBatch:
         if self.freeze_done:
             self.active &= (~done).to(torch.uint8)
         return self.reward, done, self.flags
+
+    def what_if(self, robot_actions, stream=None):
+        """`step(action, update=False)` (crowd_sim_plus.py:1025, :1239-1255) for A candidate robot actions per environment in
+        one launch: robot_actions [B, A, 2] fp64 CUDA tensor.  Returns (reward [B,A], done [B,A] bool, flags [B,A],
+        next_humans [B,H,4] = get_next_observable_state of every human, next_robot [B,A,2]); the state is not modified.
+        This is the look-ahead SARL_input_complete / RGL_multistep_input_complete run once per discrete action (:797-866)."""
+        a = robot_actions
+        if not (isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.float64 and a.is_contiguous()):
+            a = torch.as_tensor(np.asarray(a, np.float64)).to(self.device).contiguous()
+        assert a.dim() == 3 and a.shape[0] == self.B and a.shape[2] == 2
+        A = int(a.shape[1])
+        H = self.state.H
+        reward = torch.empty(self.B, A, dtype=torch.float64, device=self.device)
+        dmin = torch.empty(self.B, A, dtype=torch.float64, device=self.device)
+        flags = torch.zeros(self.B, A, dtype=torch.int32, device=self.device)
+        next_h = torch.empty(self.B, H, 4, dtype=torch.float64, device=self.device)
+        next_r = torch.empty(self.B, A, 2, dtype=torch.float64, device=self.device)
+        pc, dc, rc = self._cfgs
+        st = self.state.cstruct()
+        _capi.check(_capi.lib.snb_env_whatif(C.byref(pc), C.byref(dc), C.byref(rc), C.byref(st),
+                                             self.obstacles.handle if self.obstacles is not None else None, _capi.ptr(a), A, None,
+                                             _capi.ptr(reward), _capi.ptr(dmin), _capi.ptr(flags), _capi.ptr(next_h), _capi.ptr(next_r),
+                                             _capi.ptr(self.status), _capi.stream_ptr(stream)), "snb_env_whatif")
+        self.whatif_dmin = dmin
+        return reward, (flags & _capi.F_DONE) != 0, flags, next_h, next_r
 
     def step_host(self, robot_action_np):
         """Host-buffer form used for end-to-end timing: H2D(action) -> step -> D2H(observation, reward, flags)."""

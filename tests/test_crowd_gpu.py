@@ -275,6 +275,65 @@ def test_env_step_batch_rollout_vs_oracle(policy, B, H, segs, steps):
     assert int(status.item()) == 0
 
 
+@pytest.mark.parametrize("policy,B,H,segs,kin", [("orca", 512, 10, None, 0), ("orca_plus", 128, 6, BOTTLENECK, 1), ("sfm", 256, 25, HALLWAY, 0)])
+def test_env_whatif_equals_step_on_a_copy(policy, B, H, segs, kin):
+    """snb_env_whatif = CrowdSimPlus.step(action, update=False) for A candidate robot actions per environment
+    (crowd_sim_plus.py:1239-1255; the RL look-ahead of :797-866).  Oracle: the C restatement of step() applied to a COPY of the
+    scene, once per candidate action.  ORCA: reward / flags / next states bit-identical; SFM: 1e-8.  The state in HBM and
+    prev_dist must not change."""
+    _capi, state, _ = _snb()
+    rng = np.random.default_rng(7)
+    A = 31                                                         # 1 + 30 discrete actions (build_action_space, :275-297)
+    env = _random_env(rng, B, H, segs, spread=3.0 if segs is None else 0.8, speed=0.5, hradius=0.3 if segs is None else 0.2)
+    env.robot_kinematics = kin
+    if segs is not None:
+        env.py[:] = rng.uniform(-3.5, 3.5, B * H)
+        env.rpx[:] = rng.uniform(-0.5, 0.5, B)
+    env.prev_dist[:] = np.hypot(env.rpx - env.rgx, env.rpy - env.rgy)
+    ocfg, scfg = _pcfg_pair(policy, safety_space=0.05 if policy == "orca_plus" else 0.0)
+    orc = ol.default_reward_cfg(time_limit=2.0)
+    orc.has_progress = 1; orc.progress_factor = 0.3
+    rcfg = _capi.RewardCfg(success_reward=orc.success_reward, timeout=orc.timeout, collision_penalty=orc.collision_penalty,
+                           wall_collision_penalty=orc.wall_collision_penalty, freezing_penalty=orc.freezing_penalty,
+                           discomfort=orc.discomfort, has_progress=1, discomfort_dist=orc.discomfort_dist,
+                           discomfort_penalty_factor=orc.discomfort_penalty_factor, progress_factor=0.3, time_limit=orc.time_limit)
+    door, odoor = _capi.DoorCfg(enabled=0), ol.DoorCfg(enabled=0)
+    soa = _upload(env, kin=kin)
+    obs = state.Obstacles(segs) if segs is not None else None
+    acts = rng.uniform(-1, 1, (B, A, 2))
+    acts[:, 0] = 0.0                                                # ActionRot(0, 0): frozen
+    before = soa.to_numpy("px", "py", "vx", "vy", "gx", "gy", "ex_px", "ex_py", "rtheta", "global_time", "prev_dist")
+    a = torch.tensor(acts, dtype=torch.float64, device="cuda")
+    reward = torch.zeros(B, A, dtype=torch.float64, device="cuda"); dmin = torch.zeros_like(reward)
+    flags = torch.zeros(B, A, dtype=torch.int32, device="cuda")
+    nh = torch.zeros(B, H, 4, dtype=torch.float64, device="cuda"); nr = torch.zeros(B, A, 2, dtype=torch.float64, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = soa.cstruct()
+    _capi.check(_capi.lib.snb_env_whatif(C.byref(scfg), C.byref(door), C.byref(rcfg), C.byref(st), obs.handle if obs is not None else None,
+                                         _capi.ptr(a), A, None, _capi.ptr(reward), _capi.ptr(dmin), _capi.ptr(flags), _capi.ptr(nh),
+                                         _capi.ptr(nr), _capi.ptr(status), _capi.stream_ptr()), "snb_env_whatif")
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    after = soa.to_numpy("px", "py", "vx", "vy", "gx", "gy", "ex_px", "ex_py", "rtheta", "global_time", "prev_dist")
+    for n in before:
+        assert np.array_equal(before[n], after[n]), f"what-if modified state.{n}"
+    tol = 0.0 if policy != "sfm" else 1e-8
+    R, F, NH, NR = reward.cpu().numpy(), flags.cpu().numpy(), nh.cpu().numpy(), nr.cpu().numpy()
+    for k in range(A):
+        e2 = env.copy()
+        r_ref, d_ref, f_ref = ol.env_step(ocfg, odoor, orc, e2, np.ascontiguousarray(acts[:, k]), n_threads=8)
+        assert np.max(np.abs(NR[:, k, 0] - e2.rpx)) <= 1e-12 and np.max(np.abs(NR[:, k, 1] - e2.rpy)) <= 1e-12, k
+        assert np.max(np.abs(R[:, k] - r_ref)) <= (1e-12 if policy != "sfm" else 1e-7), k
+        if policy != "sfm":
+            assert np.array_equal(F[:, k], f_ref), k
+        else:
+            assert np.mean(F[:, k] == f_ref) > 0.995, k
+        if k == 0:
+            ref_nh = np.stack([e2.px, e2.py, e2.vx, e2.vy], -1).reshape(B, H, 4)
+            assert np.max(np.abs(NH - ref_nh)) <= tol
+    assert (F[:, 0] & _capi.F_FROZEN).all()
+
+
 def test_policy_plugin_predict_matches_oracle():
     """The B=1 plugin call: snb.policy.ORCA().predict(JointState) == what the reference's orca.py computes on the
     oracle RVO2, including the neighbour order; SFM().predict within 1e-12."""
@@ -369,3 +428,94 @@ discomfort_penalty_factor = 0.5
         assert abs(reward[0].item() - g["reward"][k]) < 1e-9
         assert int(flags[0].item()) == int(g["flags"][k])
     env.check_status()
+
+
+class _CountingRng:
+    """numpy Generator wrapper that counts the 64-bit draws the host generator consumes."""
+    def __init__(self, seed):
+        self.g, self.n = np.random.default_rng(seed), 0
+
+    def random(self):
+        self.n += 1
+        return self.g.random()
+
+    def uniform(self, a, b):
+        self.n += 1
+        return self.g.uniform(a, b)
+
+
+@pytest.mark.parametrize("rule,H,B", [("circle_crossing", 10, 1024), ("circle_crossing", 5, 64), ("hallway", 6, 256),
+                                      ("hallway_static", 5, 256), ("hallway_bottleneck", 5, 256), ("hallway_squeeze", 4, 128),
+                                      ("rectangle", 6, 128)])
+def test_scene_reset_on_device_matches_host_generator(rule, H, B):
+    """snb_scene_reset (SeedSequence + PCG64 + the reference's rejection sampling, one thread per environment) against the host
+    restatement of CrowdSimPlus.reset (snb/scenario.py, pinned to reference episodes): same number of draws per environment (=
+    identical accept / reject sequence), v_pref bit-equal (pure PCG64 arithmetic), positions / goals within 1e-12 (libm ulps)."""
+    import configparser
+    from snb import scenario
+    from snb.env import CrowdSimPlusBatch
+    cfg = configparser.RawConfigParser()
+    cfg.read_string(f"""
+[env]
+time_limit = 30
+time_step = 0.25
+val_size = 100
+test_size = 500
+randomize_attributes = true
+[sim]
+train_val_sim = {rule}
+test_sim = {rule}
+starts_moving = 0
+square_width = 5
+circle_radius = 4.0
+rect_width = 2.5
+rect_height = 4
+human_num = {H}
+[humans]
+visible = true
+policy = {'orca' if rule == 'circle_crossing' else 'orca_plus'}
+radius = 0.3
+sensor = coordinates
+safety_space = 0.05
+v_pref = 1.5
+[robot]
+visible = true
+policy = linear
+radius = 0.25
+v_pref = 1.0
+sensor = coordinates
+[reward]
+success_reward = 1
+collision_penalty = -0.25
+freezing_penalty = -0.125
+discomfort_dist = 0.2
+discomfort_penalty_factor = 0.5
+""")
+    env = CrowdSimPlusBatch(B, "cuda")
+    env.configure(cfg)
+    cases = (np.arange(B) * 7 + 3) % 500
+    env.reset('test', test_cases=cases, on_device=True)
+    torch.cuda.synchronize()
+    dev = env.state.to_numpy("px", "py", "gx", "gy", "fgx", "fgy", "vpref", "theta", "radius", "ex_px", "ex_py", "rgx", "rgy", "rtheta", "prev_dist")
+    draws = env.reset_draws.cpu().numpy()
+    p = scenario.SceneParams(env.circle_radius, env.rect_width, env.rect_height, env.human_radius, env.human_v_pref,
+                             env.robot_radius, env.rewards["discomfort_dist"], env.randomize_attributes)
+    segs, door = scenario.static_obstacles(rule, p)
+    for b in range(B):
+        rng = _CountingRng(1000 + int(cases[b]))          # test phase: offset = case_capacity['val'] = 1000
+        raw = scenario._generate_with_goals(rule, H, rng, p, segs, door)
+        assert rng.n == draws[b], (b, rng.n, draws[b])
+        for i, (px, py, fgx, fgy, v_pref, theta) in enumerate(raw):
+            gx, gy = scenario.door_goal(rule, door, len(segs), px, py, fgx, fgy)
+            got = [dev[n][b, i] for n in ("px", "py", "gx", "gy", "fgx", "fgy", "theta")]
+            assert np.max(np.abs(np.array(got) - np.array([px, py, gx, gy, fgx, fgy, theta]))) < 1e-12, (b, i)
+            assert dev["vpref"][b, i] == v_pref
+    assert np.all(dev["radius"] == 0.3) and np.all(dev["ex_py"] == -4.0) and np.all(dev["rgy"] == 4.0) and np.all(dev["prev_dist"] == 8.0)
+    # and the simulator runs from the device-built scenes exactly as from the uploaded ones
+    env2 = CrowdSimPlusBatch(B, "cuda")
+    env2.configure(cfg)
+    env2.reset('test', test_cases=cases, on_device=False)
+    a = torch.zeros(B, 2, dtype=torch.float64, device="cuda"); a[:, 1] = 1.0
+    for _ in range(5):
+        env.step(a); env2.step(a)
+    assert float((env.state.px - env2.state.px).abs().max()) < 1e-6
