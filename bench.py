@@ -259,6 +259,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernels, timed live with CUDA events on the launching stream ----
     pk = peaks()
     roof, roof_other = kernel_rooflines(den, dev, pk, B, A, S, T, NS, ms / args.steps)
+    sim_only = sim_only_lines(dev, pk, ENV_CFG) if (rank == 0 and not args.skip_sim_only) else None
 
     # ---- end-of-episode metric gather (the only collective of the path) ----
     if dist is not None:
@@ -288,6 +289,7 @@ def run_ours(args):
             "faithful_3m": faithful,
             "clocks": clocks,
             "roofline": roof, "roofline_other": roof_other,
+            "sim_only": sim_only,
             "cpu_baseline": cpu,
             "bound_note": "at sustained bf16 peak the reference semantics (S=20 cross-sample attention) bound sim+JMID at "
                           f"{pk['tf_sustained'] * 1e12 / (den.flops_per_iter() * NS):.0f} env-steps/s per GPU (BASELINE.md section 3)",
@@ -295,6 +297,60 @@ def run_ours(args):
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def sim_only_lines(dev, pk, cfg_text):
+    """The crowd step alone (SURVEY 8d (i) "sim-only"): configs[1] ORCA 1024 x 10, configs[2] SFM 4096 x 25 + hallway walls, and an
+    HBM-sized ORCA batch (2^20 envs x 10, ~1 GB of fp64 state >> L2) where the HBM roofline of the kernel is meaningful; plus the
+    callers either side of it: seeded reset on the device (8f n3) and the 31-action what-if step (8f n4).  CUDA events on the
+    launching stream, 3 warm-ups, L2 flushed between timed launches."""
+    import configparser
+    from snb.env import CrowdSimPlusBatch
+    flush = torch.empty(64 * 1024 * 1024, device=dev, dtype=torch.float32)   # 256 MB > L2
+
+    def timed(fn, reps=8):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+
+    out = {}
+    for name, B, H, policy, sim in (("orca_1024x10", 1024, 10, "orca", "circle_crossing"), ("sfm_4096x25_hallway", 4096, 25, "sfm", "hallway"),
+                                    ("orca_1048576x10", 1 << 20, 10, "orca", "circle_crossing")):
+        cfg = configparser.RawConfigParser()
+        txt = cfg_text.format(H=H).replace("policy = orca", f"policy = {policy}").replace("circle_crossing", sim)
+        if sim == "hallway":
+            txt = txt.replace("rect_width = 1.75", "rect_width = 6.0").replace("rect_height = 4", "rect_height = 12")
+        cfg.read_string(txt)
+        env = CrowdSimPlusBatch(B, dev)
+        env.configure(cfg)
+        env.freeze_done = False
+        cases = np.arange(B) % 500
+        t_reset = timed(lambda: env.reset('test', test_cases=cases), reps=3)
+        act = torch.zeros(B, 2, dtype=torch.float64, device=dev); act[:, 1] = 0.5
+        t_step = timed(lambda: env.step(act))
+        alg = (48 * H + 44) * B                                     # SURVEY 8d: fp32-accounted algorithmic bytes per launch
+        moved = (12 * 8 * H + 5 * 8 + 5 * 8 + 2 * 8) * B            # fp64 state actually read + written (humans, robot, per-env)
+        rec = {"envs": B, "humans": H, "policy": policy, "scene": sim, "env_steps_per_s": B / (t_step * 1e-3), "launch_ms": t_step,
+               "roofline": {"bound": "hbm", "achieved": alg / (t_step * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                            "frac": alg / (t_step * 1e-3) / 1e9 / pk["hbm_gbs"], "fp64_state_gbs": moved / (t_step * 1e-3) / 1e9,
+                            "note": "state fits L2: latency / occupancy bound" if moved < 100e6 else "state >> L2"},
+               "reset_on_device_ms": t_reset, "reset_envs_per_s": B / (t_reset * 1e-3)}
+        if B <= 4096:
+            A = 31
+            acts = torch.zeros(B, A, 2, dtype=torch.float64, device=dev); acts[:, 1:, 1] = 0.5
+            t_w = timed(lambda: env.what_if(acts))
+            rec["whatif_31_actions_ms"] = t_w
+            rec["whatif_env_actions_per_s"] = B * A / (t_w * 1e-3)
+        out[name] = rec
+        del env
+    return out
 
 
 def kernel_rooflines(den, dev, pk, B, A, S, T, NS, ms_per_step):
@@ -330,9 +386,12 @@ def kernel_rooflines(den, dev, pk, B, A, S, T, NS, ms_per_step):
     peak = pk["tf_burst"]
     n_chunks = (B + chunk - 1) // chunk
     attn_share = t_attn * 3 * NS * n_chunks / ms_per_step
-    roof = {"kernel": "attn_fwd_kernel (flash attention, tcgen05 SS + TS, TMEM S/P/O)", "bound": "tensor",
+    roof = {"kernel": "attn_fwd_kernel (flash attention: tcgen05 SS MMAs, S / O in TMEM, P through swizzled shared memory)", "bound": "tensor",
             "achieved": fl_attn / (t_attn * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-            "frac": fl_attn / (t_attn * 1e-3) / 1e12 / peak, "traffic": None, "peak_source": f"{pk['src']} (burst: kernel timed alone)",
+            "frac": fl_attn / (t_attn * 1e-3) / 1e12 / peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this very shape (ncu --set full, profiles/r01_ncu_attn_decoupled_chunk128.txt):
+            # 630.1 MB + 190.7 MB against 629.1 MB (QKV) + 209.7 MB (out) algorithmic -- K / V re-reads by the 7 query-pair CTAs hit L2
+            "traffic": 820.8e6 if (chunk == 128 and N == 1600) else None, "traffic_unit": "bytes per launch", "peak_source": f"{pk['src']} (burst: kernel timed alone)",
             "flops_per_launch": fl_attn, "avg_launch_ms": t_attn, "launches_per_step": 3 * NS * n_chunks,
             "share_of_step": attn_share, "shape": f"{chunk} envs x 4 heads x {N} tokens x 128"}
     other = [{"kernel": "gemm_bf16_tn_kernel<256,bias> (QKV projection, tcgen05 + TMA, persistent)", "bound": "tensor",
@@ -432,6 +491,7 @@ if __name__ == "__main__":
     ap.add_argument("--samples", type=int, default=20)
     ap.add_argument("--denoise-steps", type=int, default=20)
     ap.add_argument("--cpu-sample-envs", type=int, default=4)
+    ap.add_argument("--skip-sim-only", action="store_true", help="skip the crowd-step-only / reset / what-if side measurements")
     ap.add_argument("--attention-radius", type=float, default=1e6,
                     help="attention / cluster radius of the predictor; 1e6 = every human inside the cluster (A = H, the metric's workload), "
                          "3.0 = the shipped value")
