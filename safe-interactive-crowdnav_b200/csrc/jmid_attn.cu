@@ -24,13 +24,16 @@ constexpr float RESCALE_THRESHOLD = 8.0f; // log2 units: P <= 2^8 before the run
 struct AttnArgs {
     bf16 *out;        // [n_env * n_tok, 512]
     int n_tok;
+    int n_items;      // n_env * NHEAD * n_qp work items (environment, head, pair of 128-query tiles)
+    int n_qp;         // query-tile pairs per (environment, head)
     float scale_log2; // log2(e) / sqrt(HD)
 };
 
 #ifdef SNB_ATTN_TRACE
 // debug build only (SNB_NVCC_FLAGS=-DSNB_ATTN_TRACE): clock64() stamps of CTA (0,0,0): [role 0..4][block j < 16][event < 8]
 __device__ long long g_attn_trace[6 * 16 * 8];
-#define ATTN_TRACE(role, j, ev) do { if (trace_on && (j) < 16) g_attn_trace[((role) * 16 + (j)) * 8 + (ev)] = clock64(); } while (0)
+// stamps the SECOND work item of CTA 0 (steady state: its prologue overlaps the first item)
+#define ATTN_TRACE(role, j, ev) do { if (trace_on && w == (int)(blockIdx.x + gridDim.x) && (j) < 16) g_attn_trace[((role) * 16 + (j)) * 8 + (ev)] = clock64(); } while (0)
 #else
 #define ATTN_TRACE(role, j, ev) do { } while (0)
 #endif
@@ -72,15 +75,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
     uint64_t *q_full = bars;                               // [2] per tile
     uint64_t *kv_full = bars + 2, *kv_empty = bars + 5;    // [3] per ring slot
     uint64_t *s_full = bars + 8, *s_free = bars + 10, *p_ready = bars + 12, *pv_done = bars + 14;   // [2] per tile
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+    uint64_t *q_empty = bars + 16, *o_free = bars + 18;    // [2] per tile: Q_t may be refilled / O_t may be overwritten (next work item)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 20);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
-    const int q0 = blockIdx.x * (2 * BQ), head = blockIdx.y, env = blockIdx.z;
     const int n_tok = args.n_tok;
     const int n_kv = (n_tok + BKV - 1) / BKV;
-    const bool has_b = q0 + BQ < n_tok;                    // the second tile holds at least one real query
+    // PERSISTENT: this CTA walks the work items blockIdx.x, blockIdx.x + gridDim.x, ...  Every role runs the same loop and decodes an
+    // item the same way; all mbarrier phases come from running counters (iterations g_t = items x n_kv, items i_t, ring index c),
+    // so the next item's Q / K0 are in flight and its S(0) is issued while the softmax warps still drain O of the current one.
+    auto decode = [&](int w, int &q0, int &head, int &env, bool &has_b) {
+        const int qp = w % args.n_qp, eh = w / args.n_qp;
+        q0 = qp * (2 * BQ); head = eh % NHEAD; env = eh / NHEAD;
+        has_b = q0 + BQ < n_tok;                           // the second tile holds at least one real query
+    };
 #ifdef SNB_ATTN_TRACE
-    const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp < 4 || (warp & 3) == 0);
+    const bool trace_on = blockIdx.x == 0 && lane == 0 && (warp < 4 || (warp & 3) == 0);
     if (trace_on && warp == 0) {
         long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         g_attn_trace[5 * 128 + 0] = clock64(); g_attn_trace[5 * 128 + 3] = gt;
@@ -90,7 +100,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tmQKV);
         for (int s = 0; s < 2; ++s) {
-            tc::mbar_init(&q_full[s], 1);
+            tc::mbar_init(&q_full[s], 1); tc::mbar_init(&q_empty[s], 1); tc::mbar_init(&o_free[s], 128);
             tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_free[s], 128); tc::mbar_init(&p_ready[s], 128); tc::mbar_init(&pv_done[s], 1);
         }
         for (int s = 0; s < ATTN_RING; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1); }
@@ -108,26 +118,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
         setmaxnreg_dec<88>();
         if (warp == 0 && lane == 0) {
             // ===================== TMA producer =====================
-            const int cq = head * HD, ck = 512 + head * HD, cv = 1024 + head * HD;
-            for (int t = 0; t < (has_b ? 2 : 1); ++t) {
-                tc::mbar_arrive_expect_tx(&q_full[t], TILE_BYTES);
-                tc::tma_load_3d(sQ + t * TILE_BYTES, &tmQKV, &q_full[t], cq, q0 + t * BQ, env);
-                tc::tma_load_3d(sQ + t * TILE_BYTES + TILE_BYTES / 2, &tmQKV, &q_full[t], cq + 64, q0 + t * BQ, env);
-            }
-            int c = 0;                                   // running index into the K0, K1, V0, K2, V1, ... sequence
-            auto load = [&](int col, int j) {
-                const int slot = c % ATTN_RING;
-                const uint32_t ph = (c / ATTN_RING) & 1;
-                ++c;
-                tc::mbar_wait(&kv_empty[slot], ph ^ 1);
-                tc::mbar_arrive_expect_tx(&kv_full[slot], TILE_BYTES);
-                tc::tma_load_3d(sKV + slot * TILE_BYTES, &tmQKV, &kv_full[slot], col, j * BKV, env);
-                tc::tma_load_3d(sKV + slot * TILE_BYTES + TILE_BYTES / 2, &tmQKV, &kv_full[slot], col + 64, j * BKV, env);
-            };
-            load(ck, 0);
-            for (int j = 0; j < n_kv; ++j) {
-                if (j + 1 < n_kv) load(ck, j + 1);
-                load(cv, j);
+            int c = 0;                                   // running index into the K0, K1, V0, K2, V1, ... sequence (all items)
+            int it[2] = {0, 0};                          // items tile t has taken part in
+            for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
+                int q0, head, env; bool has_b;
+                decode(w, q0, head, env, has_b);
+                const int cq = head * HD, ck = 512 + head * HD, cv = 1024 + head * HD;
+                for (int t = 0; t < (has_b ? 2 : 1); ++t) {
+                    tc::mbar_wait(&q_empty[t], (it[t] & 1) ^ 1);     // the previous item's last S_t has read Q_t
+                    ++it[t];
+                    tc::mbar_arrive_expect_tx(&q_full[t], TILE_BYTES);
+                    tc::tma_load_3d(sQ + t * TILE_BYTES, &tmQKV, &q_full[t], cq, q0 + t * BQ, env);
+                    tc::tma_load_3d(sQ + t * TILE_BYTES + TILE_BYTES / 2, &tmQKV, &q_full[t], cq + 64, q0 + t * BQ, env);
+                }
+                auto load = [&](int col, int j) {
+                    const int slot = c % ATTN_RING;
+                    const uint32_t ph = (c / ATTN_RING) & 1;
+                    ++c;
+                    tc::mbar_wait(&kv_empty[slot], ph ^ 1);
+                    tc::mbar_arrive_expect_tx(&kv_full[slot], TILE_BYTES);
+                    tc::tma_load_3d(sKV + slot * TILE_BYTES, &tmQKV, &kv_full[slot], col, j * BKV, env);
+                    tc::tma_load_3d(sKV + slot * TILE_BYTES + TILE_BYTES / 2, &tmQKV, &kv_full[slot], col + 64, j * BKV, env);
+                };
+                load(ck, 0);
+                for (int j = 0; j < n_kv; ++j) {
+                    if (j + 1 < n_kv) load(ck, j + 1);
+                    load(cv, j);
+                }
             }
         } else if (warp == 1) {
           // ===================== MMA issuer =====================
@@ -184,47 +201,45 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
                 ++c;
                 tc::mbar_wait(&kv_full[slot], ph);
             };
-            tc::mbar_wait(&q_full[0], 0);
-            next_tile();                                 // K0
-            tc::tc_fence_after();
-            issue_S(0, slot, 0);
-            if (has_b) {
-                tc::mbar_wait(&q_full[1], 0);
-                tc::tc_fence_after();
-                issue_S(1, slot, 0);
-            }
-            tc::umma_commit(&kv_empty[slot]);
-            for (int j = 0; j < n_kv; ++j) {
-                const uint32_t ph = j & 1;
-                if (j + 1 < n_kv) {                      // S(j+1) of both tiles as soon as the softmax warps hold S(j) in registers
-                    next_tile();                         // K(j+1)
-                    tc::mbar_wait(&s_free[0], ph);
+            int g[2] = {0, 0}, it[2] = {0, 0};           // per tile: iterations / items done so far (barrier phases)
+            for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
+                int q0, head, env; bool has_b;
+                decode(w, q0, head, env, has_b);
+                const int nt = has_b ? 2 : 1;
+                next_tile();                             // K0
+                for (int t = 0; t < nt; ++t) {
+                    tc::mbar_wait(&q_full[t], it[t] & 1);
+                    if (g[t] > 0) tc::mbar_wait(&s_free[t], (g[t] - 1) & 1);   // the previous item's last S_t is in registers
                     tc::tc_fence_after();
-                    ATTN_TRACE(4, j, 0);
-                    issue_S(0, slot, j + 1);
-                    ATTN_TRACE(4, j, 1);
-                    if (has_b) {
-                        tc::mbar_wait(&s_free[1], ph);
-                        tc::tc_fence_after();
-                        issue_S(1, slot, j + 1);
-                    }
-                    ATTN_TRACE(4, j, 2);
-                    tc::umma_commit(&kv_empty[slot]);
-                }
-                next_tile();                             // V(j)
-                tc::mbar_wait(&p_ready[0], ph);
-                tc::tc_fence_after();
-                ATTN_TRACE(4, j, 3);
-                issue_PV(0, slot, j);
-                ATTN_TRACE(4, j, 4);
-                if (has_b) {
-                    tc::mbar_wait(&p_ready[1], ph);
-                    tc::tc_fence_after();
-                    ATTN_TRACE(4, j, 5);
-                    issue_PV(1, slot, j);
-                    ATTN_TRACE(4, j, 6);
+                    issue_S(t, slot, 0);
+                    if (n_kv == 1) tc::umma_commit(&q_empty[t]);
                 }
                 tc::umma_commit(&kv_empty[slot]);
+                for (int j = 0; j < n_kv; ++j) {
+                    if (j + 1 < n_kv) {                      // S(j+1) of both tiles as soon as the softmax warps hold S(j) in registers
+                        next_tile();                         // K(j+1)
+                        for (int t = 0; t < nt; ++t) {
+                            tc::mbar_wait(&s_free[t], (g[t] + j) & 1);
+                            tc::tc_fence_after();
+                            if (t == 0) ATTN_TRACE(4, j, 0);
+                            issue_S(t, slot, j + 1);
+                            if (j + 2 == n_kv) tc::umma_commit(&q_empty[t]);   // that was the item's last use of Q_t
+                        }
+                        tc::umma_commit(&kv_empty[slot]);
+                        ATTN_TRACE(4, j, 2);
+                    }
+                    next_tile();                             // V(j)
+                    for (int t = 0; t < nt; ++t) {
+                        if (j == 0) tc::mbar_wait(&o_free[t], (it[t] & 1) ^ 1);   // the previous item's O_t has been written out
+                        tc::mbar_wait(&p_ready[t], (g[t] + j) & 1);
+                        tc::tc_fence_after();
+                        ATTN_TRACE(4, j, 3 + 2 * t);
+                        issue_PV(t, slot, j);
+                        ATTN_TRACE(4, j, 4 + 2 * t);
+                    }
+                    tc::umma_commit(&kv_empty[slot]);
+                }
+                for (int t = 0; t < nt; ++t) { g[t] += n_kv; ++it[t]; }
             }
           }
         }
@@ -232,21 +247,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
         setmaxnreg_inc<208>();
         // ===================== softmax / correction / epilogue of tile t =====================
         const int t = (warp - 4) >> 2;
-        if (t == 0 || has_b) {
-            const uint32_t tmem_base = *tmem_slot;
-            const int quarter = warp & 3;
-            const int row_in_tile = quarter * 32 + lane;
-            const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
-            const uint32_t s_addr = tmem_base + lane_addr + TM_S + t * 128;
-            const uint32_t o_addr = tmem_base + lane_addr + TM_O + t * 128;
-            // my row of P: 128-byte rows inside 1024-byte 8-row atoms, 16-byte chunk index XORed with (row & 7) (SWIZZLE_128B)
-            uint8_t *p_row = sP + t * TILE_BYTES + row_in_tile * 128;
-            const int sw = row_in_tile & 7;
-            const float c = args.scale_log2;
+        const uint32_t tmem_base = *tmem_slot;
+        const int quarter = warp & 3;
+        const int row_in_tile = quarter * 32 + lane;
+        const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
+        const uint32_t s_addr = tmem_base + lane_addr + TM_S + t * 128;
+        const uint32_t o_addr = tmem_base + lane_addr + TM_O + t * 128;
+        // my row of P: 128-byte rows inside 1024-byte 8-row atoms, 16-byte chunk index XORed with (row & 7) (SWIZZLE_128B)
+        uint8_t *p_row = sP + t * TILE_BYTES + row_in_tile * 128;
+        const int sw = row_in_tile & 7;
+        const float c = args.scale_log2;
+        int g = 0;                    // iterations of this tile so far: every per-tile barrier completes one phase per iteration
+        for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
+            int q0, head, env; bool has_b;
+            decode(w, q0, head, env, has_b);
+            if (t == 1 && !has_b) continue;
             float m_used = -INFINITY; // running max the exponents are taken against (raw score units)
             float l = 0.0f;
             for (int j = 0; j < n_kv; ++j) {
-                const uint32_t ph = j & 1;
+                const uint32_t ph = (g + j) & 1;
                 ATTN_TRACE(t, j, 0);
                 tc::mbar_wait(&s_full[t], ph);
                 ATTN_TRACE(t, j, 1);
@@ -284,7 +303,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
                 } else if (__any_sync(0xffffffffu, (bmax - m_used) * c > RESCALE_THRESHOLD)) {
                     // Refresh the running max.  The decision is WARP-uniform (tcgen05.ld/st are .sync.aligned and must be
                     // executed by all 32 lanes together); lanes whose own max did not grow rescale by exactly 1.
-                    tc::mbar_wait(&pv_done[t], (j - 1) & 1);              // O_t is stable once PV_t(j-1) has landed
+                    tc::mbar_wait(&pv_done[t], ph ^ 1);                   // O_t is stable once PV_t(j-1) has landed
                     __syncwarp();
                     tc::tc_fence_after();
                     const float m_new = fmaxf(m_used, bmax);
@@ -335,7 +354,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
                 }
                 ATTN_TRACE(t, j, 3);
                 // ... then the P row goes to shared memory once PV_t(j-1) has consumed the previous one (normally long ago)
-                if (j > 0) tc::mbar_wait(&pv_done[t], (j - 1) & 1);
+                if (g + j > 0) tc::mbar_wait(&pv_done[t], ph ^ 1);   // (for j == 0: the previous item's last PV, already awaited by its epilogue)
                 auto store = [&](const uint32_t (&s)[32], int box, int chunk0) {   // 32 keys = four 16-byte chunks of my P row
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
@@ -349,7 +368,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
                 ATTN_TRACE(t, j, 5);
             }
             // final: O / l -> global
-            tc::mbar_wait(&pv_done[t], (n_kv - 1) & 1);
+            tc::mbar_wait(&pv_done[t], (g + n_kv - 1) & 1);
             __syncwarp();
             tc::tc_fence_after();
             const float inv_l = 1.0f / l;
@@ -374,6 +393,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
                 }
             }
             tc::tc_fence_before();
+            tc::mbar_arrive(&o_free[t]);      // O_t may be overwritten by the next item's first PV
+            g += n_kv;
         }
     }
     __syncthreads();
@@ -446,7 +467,15 @@ int snb_attn_launch(const AttnPlan *plan, bf16 *out, cudaStream_t stream)
     AttnArgs a;
     a.out = out; a.n_tok = plan->n_tok;
     a.scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
-    dim3 grid((plan->n_tok + 2 * BQ - 1) / (2 * BQ), NHEAD, plan->n_env);
+    a.n_qp = (plan->n_tok + 2 * BQ - 1) / (2 * BQ);
+    a.n_items = a.n_qp * NHEAD * plan->n_env;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        SNB_CUDA_TRY(cudaGetDevice(&dev));
+        SNB_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int grid = a.n_items < num_sms ? a.n_items : num_sms;   // persistent: one CTA per SM walks the item list
     attn_fwd_kernel<<<grid, ATTN_THREADS, ATTN_SMEM, stream>>>(plan->tmQKV, a);
     snb_count_launch();
     SNB_CUDA_TRY(cudaGetLastError());

@@ -48,9 +48,11 @@ def test_tcgen05_gemm_matches_fp32_matmul(M, N, K, epi):
     assert (out.float() - ref).abs().max().item() <= tol
 
 
-@pytest.mark.parametrize("n_env,n_tok", [(1, 128), (2, 256), (2, 96), (1, 200), (3, 8), (2, 1600), (1, 2400)])
+@pytest.mark.parametrize("n_env,n_tok", [(1, 128), (2, 256), (2, 96), (1, 200), (3, 8), (2, 1600), (1, 2400), (60, 300), (14, 1600), (200, 72)])
 def test_flash_attention_matches_fp32_softmax(n_env, n_tok):
-    """Full unmasked sequences incl. ragged tails (n_tok not a multiple of the 128-key block) and the C4 length 1600."""
+    """Full unmasked sequences incl. ragged tails (n_tok not a multiple of the 128-key block) and the C4 length 1600; the last three
+    shapes give every persistent CTA several work items (odd and even block counts, with and without a second query tile), so the
+    running mbarrier phases across items are exercised."""
     c = _capi()
     torch.manual_seed(n_tok)
     qkv = torch.randn(n_env, n_tok, 1536, device="cuda").bfloat16()
