@@ -278,7 +278,7 @@ def run_ours(args):
             "config": {"workload": f"configs[1]+configs[3]: CrowdSimPlus ORCA step {B} envs x {H} humans + JMID {S} samples x {NS} DDIM "
                                    f"iterations per env-step ({A * S * T} tokens/env, cross-sample attention), per GPU",
                        "envs_per_gpu": B, "humans": H, "samples": S, "denoise_steps": NS, "tokens_per_env": A * S * T,
-                       "l2_policy": "inputs larger than L2: the activations of one step (> 3 GB per 128-env chunk) exceed the 126 MB L2",
+                       "l2_policy": "inputs larger than L2: the activations of one step (8 GB per 512-env chunk) exceed the 126 MB L2",
                        "context": "computed on device from the 6-frame history rings (clustering, scene graph, LSTM encoder)",
                        "attention_radius": args.attention_radius, "mean_cluster_size": mean_cluster,
                        "attention_radius_note": "default 1e6 puts all 10 humans inside the attention cluster (configs[3]: A = H = 10, the "
@@ -357,7 +357,7 @@ def kernel_rooflines(den, dev, pk, B, A, S, T, NS, ms_per_step):
     """Average launch duration of the attention kernel and of the largest GEMM at the shapes the step uses (one chunk
     of 16 envs), CUDA events on the launching stream, after warm-up."""
     from snb import _capi
-    chunk = min(B, int(os.environ.get("SNB_JMID_CHUNK", 128)))
+    chunk = min(B, int(os.environ.get("SNB_JMID_CHUNK", 512)))
     N = A * S * T
     M = chunk * N
     qkv = torch.randn(chunk, N, 1536, device=dev).bfloat16()
@@ -389,14 +389,16 @@ def kernel_rooflines(den, dev, pk, B, A, S, T, NS, ms_per_step):
     roof = {"kernel": "attn_fwd_kernel (flash attention: tcgen05 SS MMAs, S / O in TMEM, P through swizzled shared memory)", "bound": "tensor",
             "achieved": fl_attn / (t_attn * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
             "frac": fl_attn / (t_attn * 1e-3) / 1e12 / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this very shape (ncu --set full, profiles/r01_ncu_attn_decoupled_chunk128.txt):
-            # 630.1 MB + 190.7 MB against 629.1 MB (QKV) + 209.7 MB (out) algorithmic -- K / V re-reads by the 7 query-pair CTAs hit L2
-            "traffic": 820.8e6 if (chunk == 128 and N == 1600) else None, "traffic_unit": "bytes per launch", "peak_source": f"{pk['src']} (burst: kernel timed alone)",
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this very shape (ncu --set full, profiles/r01_ncu_attn_persistent_chunk512.txt):
+            # 2.523 GB + 0.819 GB against 2.517 GB (QKV) + 0.839 GB (out) algorithmic -- K / V re-reads by the 7 query-pair items hit L2
+            "traffic": 3341.6e6 if (chunk == 512 and N == 1600) else None, "traffic_unit": "bytes per launch", "peak_source": f"{pk['src']} (burst: kernel timed alone)",
             "flops_per_launch": fl_attn, "avg_launch_ms": t_attn, "launches_per_step": 3 * NS * n_chunks,
             "share_of_step": attn_share, "shape": f"{chunk} envs x 4 heads x {N} tokens x 128"}
-    other = [{"kernel": "gemm_bf16_tn_kernel<256,bias> (QKV projection, tcgen05 + TMA, persistent)", "bound": "tensor",
+    other = [{"kernel": "gemm2_bf16_tn_kernel<256,bias> (QKV projection, tcgen05 cta_group::2 + TMA, persistent)", "bound": "tensor",
               "achieved": fl_gemm / (t_gemm * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-              "frac": fl_gemm / (t_gemm * 1e-3) / 1e12 / peak, "traffic": None, "avg_launch_ms": t_gemm,
+              "frac": fl_gemm / (t_gemm * 1e-3) / 1e12 / peak,
+              # ncu (profiles/r01_ncu_gemm_chunk512.txt): 0.864 GB read + 2.468 GB written; algorithmic 0.839 + 0.002 + 2.517 GB; tensor pipe 84 % of peak cycles
+              "traffic": 3331.6e6 if M == 819200 else None, "avg_launch_ms": t_gemm,
               "shape": f"M={M} N=1536 K=512"},
              {"kernel": "whole step (all kernels)", "bound": "tensor", "achieved": den.flops_per_iter() * NS * B / (ms_per_step * 1e-3) / 1e12,
               "peak": pk["tf_sustained"], "unit": "TFLOP/s",

@@ -167,7 +167,7 @@ extern "C" int snb_jmid_create(SnbJmid **out, const SnbJmidWeights *w, int32_t m
     h->A = A; h->S = S; h->T = T; h->joint = joint ? 1 : 0; h->max_envs = max_envs; h->N = A * S * T;
     SNB_CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev));
     const char *ce = getenv("SNB_JMID_CHUNK");
-    int chunk = ce ? atoi(ce) : 128;
+    int chunk = ce ? atoi(ce) : 512;   // envs per chunk: 512 x 1600 tokens = 8 GB of activations; +2.5 % over 128 on the same box (r01)
     if (chunk < 1) chunk = 1;
     h->chunk_envs = chunk < max_envs ? chunk : max_envs;
     int rc = 0;
