@@ -139,6 +139,9 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # everything (torch ops and libsnb launches) runs on one explicit, capturable stream: the denoiser replays a CUDA graph per chunk and
+    # forks LayerNorm slabs to a side stream only when it is given a real stream (the legacy default stream cannot be captured)
+    torch.cuda.set_stream(torch.cuda.Stream(dev))
     dist = None
     if world > 1:
         import torch.distributed as dist
