@@ -519,3 +519,116 @@ discomfort_penalty_factor = 0.5
     for _ in range(5):
         env.step(a); env2.step(a)
     assert float((env.state.px - env2.state.px).abs().max()) < 1e-6
+
+
+def test_scene_reset_gives_up_loudly_on_an_overcrowded_scene():
+    """25 humans cannot be placed on a 4 m circle with 0.8 m clearance from every position AND goal: the reference's rejection
+    sampling spins forever; snb_scene_reset stops after 200 000 tries per human, reports -1 draws and reset() raises."""
+    import configparser
+    from snb import _capi
+    from snb.env import CrowdSimPlusBatch
+    cfg = configparser.RawConfigParser()
+    cfg.read_string("""
+[env]
+time_limit = 30
+time_step = 0.25
+val_size = 100
+test_size = 500
+randomize_attributes = true
+[sim]
+train_val_sim = circle_crossing
+test_sim = circle_crossing
+starts_moving = 0
+square_width = 5
+circle_radius = 4.0
+rect_width = 2.5
+rect_height = 4
+human_num = 25
+[humans]
+visible = true
+policy = orca
+radius = 0.3
+sensor = coordinates
+safety_space = 0.05
+v_pref = 1.5
+[robot]
+visible = true
+policy = linear
+radius = 0.25
+v_pref = 1.0
+sensor = coordinates
+[reward]
+success_reward = 1
+collision_penalty = -0.25
+freezing_penalty = -0.125
+discomfort_dist = 0.2
+discomfort_penalty_factor = 0.5
+""")
+    env = CrowdSimPlusBatch(4, "cuda")
+    env.configure(cfg)
+    with pytest.raises(_capi.SnbError, match="gave up"):
+        env.reset('test', test_cases=[0, 1, 2, 3])
+    assert int(env.reset_draws.min().item()) == -1
+
+
+def test_whatif_through_the_batch_env_matches_a_committed_step():
+    """CrowdSimPlusBatch.what_if(actions)[:, k] == what step(actions[:, k]) then returns, for every candidate k (ORCA, bit-exact),
+    and the environment can still be stepped afterwards."""
+    import configparser
+    from snb.env import CrowdSimPlusBatch
+    cfg = configparser.RawConfigParser()
+    cfg.read_string("""
+[env]
+time_limit = 30
+time_step = 0.25
+val_size = 100
+test_size = 500
+randomize_attributes = true
+[sim]
+train_val_sim = circle_crossing
+test_sim = circle_crossing
+starts_moving = 10
+square_width = 5
+circle_radius = 4.0
+rect_width = 2.5
+rect_height = 4
+human_num = 8
+[humans]
+visible = true
+policy = orca
+radius = 0.3
+sensor = coordinates
+safety_space = 0.05
+v_pref = 1.5
+[robot]
+visible = true
+policy = linear
+radius = 0.25
+v_pref = 1.0
+sensor = coordinates
+[reward]
+success_reward = 1
+collision_penalty = -0.25
+freezing_penalty = -0.125
+discomfort_dist = 0.2
+discomfort_penalty_factor = 0.5
+""")
+    B, A = 64, 5
+    env = CrowdSimPlusBatch(B, "cuda")
+    env.configure(cfg)
+    env.reset('test')
+    rng = np.random.default_rng(3)
+    acts = torch.tensor(rng.uniform(-1, 1, (B, A, 2)), dtype=torch.float64, device="cuda")
+    reward, done, flags, next_h, next_r = env.what_if(acts)
+    torch.cuda.synchronize()
+    for k in range(A):
+        e2 = CrowdSimPlusBatch(B, "cuda")
+        e2.configure(cfg)
+        e2.reset('test')
+        r2, d2, f2 = e2.step(acts[:, k].contiguous())
+        torch.cuda.synchronize()
+        assert torch.equal(r2, reward[:, k]) and torch.equal(f2, flags[:, k]) and torch.equal(d2, done[:, k])
+        assert torch.equal(e2.state.px, next_h[:, :, 0]) and torch.equal(e2.state.vy, next_h[:, :, 3])
+        assert torch.equal(e2.state.rpx, next_r[:, k, 0]) and torch.equal(e2.state.rpy, next_r[:, k, 1])
+    env.step(acts[:, 0].contiguous())
+    env.check_status()
