@@ -518,7 +518,7 @@ if __name__ == "__main__":
     ap.add_argument("--humans", type=int, default=10)
     ap.add_argument("--samples", type=int, default=20)
     ap.add_argument("--denoise-steps", type=int, default=20)
-    ap.add_argument("--cpu-sample-envs", type=int, default=4)
+    ap.add_argument("--cpu-sample-envs", type=int, default=12, help="envs of the workload the CPU port steps per sample (~1 s each on 16 cores)")
     ap.add_argument("--skip-sim-only", action="store_true", help="skip the crowd-step-only / reset / what-if side measurements")
     ap.add_argument("--attention-radius", type=float, default=1e6,
                     help="attention / cluster radius of the predictor; 1e6 = every human inside the cluster (A = H, the metric's workload), "
