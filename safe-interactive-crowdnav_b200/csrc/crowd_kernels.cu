@@ -16,6 +16,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -191,6 +192,7 @@ struct CrowdParams {
     int n_actions; // full_step == 2: robot_action is [B, n_actions, 2]; reward / dmin / flags are [B, n_actions]
     double *next_h;     // full_step == 2: [B, H, 4] next observable human states (px, py, vx, vy)
     double *next_robot; // full_step == 2: [B, n_actions, 2] constrained next robot position (optional)
+    int thread_mode;    // ORCA phase 1: 0 = one warp per human (small launches), 1 = one thread per human (large batches)
 };
 
 struct Line { float px, py, dx, dy; };
@@ -778,6 +780,216 @@ __device__ void orca_predict_warp(const CrowdParams &P, const Tile &T, WarpScrat
     out_vx = rx; out_vy = ry;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Thread-serial ORCA (large batches): ONE THREAD per human runs RVO2's computeNeighbors + computeNewVelocity exactly as the
+// sequential program does (Agent.cpp linearProgram1 / 2 / 3) -- same float operations in the same order as
+// the warp-cooperative path above, hence the same bits.  The warp path minimises the latency of one small launch (32 lanes
+// share one human); this path maximises throughput when there are enough humans to give every thread its own (ncu of the
+// warp path at 262 144 envs: 24 % of the warp slots occupied, issue slots 43 % busy, most lanes idle behind <= 10 neighbours).
+__device__ bool lp1_serial(const Line *lines, int lineNo, float radius, float optx, float opty, bool dirOpt, float &rx, float &ry)
+{
+    const Line li = lines[lineNo];
+    const float dotProduct = dot2(li.px, li.py, li.dx, li.dy);
+    const float discriminant = dotProduct * dotProduct + radius * radius - dot2(li.px, li.py, li.px, li.py);
+    if (discriminant < 0.0f) return false;
+    const float sq = sqrtf(discriminant);
+    float tLeft = -dotProduct - sq;
+    float tRight = -dotProduct + sq;
+    for (int j = 0; j < lineNo; ++j) {
+        const Line lj = lines[j];
+        const float denominator = det2(li.dx, li.dy, lj.dx, lj.dy);
+        const float numerator = det2(lj.dx, lj.dy, li.px - lj.px, li.py - lj.py);
+        if (fabsf(denominator) <= RVO_EPSILON) {
+            if (numerator < 0.0f) return false;
+            continue;
+        }
+        const float t = numerator / denominator;
+        if (denominator >= 0.0f) tRight = fminf(tRight, t);
+        else tLeft = fmaxf(tLeft, t);
+        if (tLeft > tRight) return false;
+    }
+    if (dirOpt) {
+        if (dot2(optx, opty, li.dx, li.dy) > 0.0f) { rx = li.px + tRight * li.dx; ry = li.py + tRight * li.dy; }
+        else { rx = li.px + tLeft * li.dx; ry = li.py + tLeft * li.dy; }
+    } else {
+        const float t = dot2(li.dx, li.dy, optx - li.px, opty - li.py);
+        if (t < tLeft) { rx = li.px + tLeft * li.dx; ry = li.py + tLeft * li.dy; }
+        else if (t > tRight) { rx = li.px + tRight * li.dx; ry = li.py + tRight * li.dy; }
+        else { rx = li.px + t * li.dx; ry = li.py + t * li.dy; }
+    }
+    return true;
+}
+
+__device__ int lp2_serial(const Line *lines, int n, float radius, float optx, float opty, bool dirOpt, float &rx, float &ry)
+{
+    if (dirOpt) { rx = optx * radius; ry = opty * radius; }
+    else if (dot2(optx, opty, optx, opty) > radius * radius) {
+        const float inv = 1.0f / sqrtf(dot2(optx, opty, optx, opty));
+        const float nx = optx * inv, ny = opty * inv;
+        rx = nx * radius; ry = ny * radius;
+    } else { rx = optx; ry = opty; }
+    for (int i = 0; i < n; ++i) {
+        if (det2(lines[i].dx, lines[i].dy, lines[i].px - rx, lines[i].py - ry) > 0.0f) {
+            const float tx = rx, ty = ry;
+            if (!lp1_serial(lines, i, radius, optx, opty, dirOpt, rx, ry)) { rx = tx; ry = ty; return i; }
+        }
+    }
+    return n;
+}
+
+__device__ void lp3_serial(const Line *lines, int n, int numObstLines, int beginLine, float radius, float &rx, float &ry, Line *proj)
+{
+    float distance = 0.0f;
+    for (int i = beginLine; i < n; ++i) {
+        const Line li = lines[i];
+        if (det2(li.dx, li.dy, li.px - rx, li.py - ry) > distance) {
+            int np = 0;
+            for (int j = 0; j < numObstLines; ++j) proj[np++] = lines[j];
+            for (int j = numObstLines; j < i; ++j) {
+                const Line lj = lines[j];
+                Line pl;
+                const float determinant = det2(li.dx, li.dy, lj.dx, lj.dy);
+                if (fabsf(determinant) <= RVO_EPSILON) {
+                    if (dot2(li.dx, li.dy, lj.dx, lj.dy) > 0.0f) continue;
+                    pl.px = 0.5f * (li.px + lj.px); pl.py = 0.5f * (li.py + lj.py);
+                } else {
+                    const float sv = det2(lj.dx, lj.dy, li.px - lj.px, li.py - lj.py) / determinant;
+                    pl.px = li.px + sv * li.dx; pl.py = li.py + sv * li.dy;
+                }
+                const float vx = lj.dx - li.dx, vy = lj.dy - li.dy;
+                const float inv = 1.0f / sqrtf(dot2(vx, vy, vx, vy));
+                pl.dx = vx * inv; pl.dy = vy * inv;
+                proj[np++] = pl;
+            }
+            const float tx = rx, ty = ry;
+            if (lp2_serial(proj, np, radius, -li.dy, li.dx, true, rx, ry) < np) { rx = tx; ry = ty; }
+            distance = det2(li.dx, li.dy, li.px - rx, li.py - ry);
+        }
+    }
+}
+
+__device__ void orca_predict_thread(const CrowdParams &P, const Tile &T, int e, int i, int genv, float &out_vx, float &out_vy)
+{
+    const SnbPolicyCfg &cfg = P.cfg;
+    const int H = P.st.H, E = P.st.E;
+    const int n_others = H - 1 + P.st.n_obs_extras;
+    const int k = e * H + i;
+    const double dpx = T.px[k], dpy = T.py[k];
+    const float px = (float)dpx, py = (float)dpy, vx = (float)T.vx[k], vy = (float)T.vy[k];
+    const float radius = (float)(T.rad[k] + 0.01 + cfg.safety_space);   // orca.py:100
+    const float maxSpeed = (float)T.vpref[k];
+    const float neighborDist = (float)cfg.neighbor_dist;
+    const float timeHorizon = (float)cfg.time_horizon, timeHorizonObst = (float)cfg.time_horizon_obst;
+    const float timeStep = (float)cfg.time_step;
+    const int maxNeighbors = cfg.max_neighbors;
+
+    // preferred velocity in double, then narrowed (orca.py:113-123 / orca_plus.py:68-79)
+    const double dvx = T.gx[k] - dpx, dvy = T.gy[k] - dpy;
+    const double speed = sqrt(fma(dvy, dvy, dvx * dvx)); // np.linalg.norm: BLAS dot fuses
+    double pvx, pvy;
+    if (cfg.policy == SNB_POLICY_ORCA_PLUS) {
+        const double vp = T.vpref[k] - 1e-3;
+        if (speed > vp) { pvx = dvx / speed * vp; pvy = dvy / speed * vp; } else { pvx = dvx; pvy = dvy; }
+    } else {
+        if (speed > 1) { pvx = dvx / speed; pvy = dvy / speed; } else { pvx = dvx; pvy = dvy; }
+    }
+    const float prefx = (float)pvx, prefy = (float)pvy;
+
+    // ---- agent neighbours: the (<= maxNeighbors) nearest inside neighborDist, sorted by (distSq, RVO2 visit order) ----
+    float dsq[SNB_MAX_AGENTS_PER_ENV];
+    unsigned inmask = 0;
+    for (int c = 0; c < n_others; ++c) {
+        double a, b, cc, d, r;
+        int id;
+        load_other(T, H, E, e, i, c, a, b, cc, d, r, id);
+        const float ddx = px - (float)a, ddy = py - (float)b;
+        dsq[c] = dot2(ddx, ddy, ddx, ddy);
+        if (maxNeighbors > 0 && dsq[c] < neighborDist * neighborDist) inmask |= 1u << c;
+    }
+    bool tie = false;
+    for (int c = 0; c < n_others && !tie; ++c)
+        for (int j = c + 1; j < n_others; ++j)
+            if (((inmask >> c) & 1u) && ((inmask >> j) & 1u) && dsq[j] == dsq[c]) { tie = true; break; }
+    unsigned char vrank[SNB_MAX_AGENTS_PER_ENV + 4];
+    const bool use_visit = tie && n_others + 1 > 10;
+    if (use_visit) {
+        // exact distance tie in a simulator with a split kd-tree: order the tied agents by RVO2's visit sequence
+        float ax[SNB_MAX_AGENTS_PER_ENV + 1], ay[SNB_MAX_AGENTS_PER_ENV + 1];
+        ax[0] = px; ay[0] = py;
+        for (int c = 0; c < n_others; ++c) {
+            double a, b, cc, d, r;
+            int id;
+            load_other(T, H, E, e, i, c, a, b, cc, d, r, id);
+            ax[c + 1] = (float)a; ay[c + 1] = (float)b;
+        }
+        kd_visit_rank(n_others + 1, ax, ay, vrank);
+    }
+    const int n_in = __popc(inmask);
+    const int n_nb = n_in < maxNeighbors ? n_in : maxNeighbors;
+    int nb[SNB_MAX_AGENTS_PER_ENV];
+    for (int c = 0; c < n_others; ++c) {
+        if (!((inmask >> c) & 1u)) continue;
+        int rank = 0;
+        for (int j = 0; j < n_others; ++j) {
+            if (!((inmask >> j) & 1u)) continue;
+            const bool before = use_visit ? (vrank[j + 1] < vrank[c + 1]) : (j < c);
+            if (dsq[j] < dsq[c] || (dsq[j] == dsq[c] && before)) ++rank;
+        }
+        if (rank < n_nb) nb[rank] = c;
+    }
+    if (P.nbr_cnt) P.nbr_cnt[genv * H + i] = n_nb;
+
+    Line lines[SNB_MAX_ORCA_LINES];
+    // ---- obstacle neighbours and lines (ORCAPlus only) ----
+    int numObstLines = 0;
+    bool overflow = false;
+    if (cfg.policy == SNB_POLICY_ORCA_PLUS && P.n_vert > 0) {
+        int obst_ids[SNB_MAX_ORCA_LINES];
+        float obst_ds[SNB_MAX_ORCA_LINES];
+        const float rs = timeHorizonObst * maxSpeed + radius;
+        int n_on = obstacle_neighbors(P.verts, P.nodes, P.bsp_root, px, py, rs * rs, obst_ids, obst_ds);
+        if (n_on < 0) { overflow = true; n_on = 0; }
+        const float invT = 1.0f / timeHorizonObst;
+        for (int q = 0; q < n_on; ++q) {
+            const int o1 = obst_ids[q];
+            const ObstVert a = P.verts[o1], b = P.verts[a.next];
+            const float r1x = a.px - px, r1y = a.py - py, r2x = b.px - px, r2y = b.py - py;
+            bool covered = false;
+            for (int j = 0; j < numObstLines && !covered; ++j)
+                covered = (det2(invT * r1x - lines[j].px, invT * r1y - lines[j].py, lines[j].dx, lines[j].dy) - invT * radius >= -RVO_EPSILON) &&
+                          (det2(invT * r2x - lines[j].px, invT * r2y - lines[j].py, lines[j].dx, lines[j].dy) - invT * radius >= -RVO_EPSILON);
+            if (covered) continue;
+            Line cand;
+            if (obstacle_orca_line(P.verts, o1, px, py, vx, vy, radius, invT, cand)) {
+                if (numObstLines < SNB_MAX_ORCA_LINES) lines[numObstLines++] = cand; else overflow = true;
+            }
+        }
+    }
+
+    // ---- agent lines ----
+    int nLines = numObstLines + n_nb;
+    if (nLines > SNB_MAX_ORCA_LINES) { overflow = true; nLines = SNB_MAX_ORCA_LINES; }
+    for (int r = 0; r < n_nb; ++r) {
+        double a, b, cc, d, rr;
+        int id;
+        load_other(T, H, E, e, i, nb[r], a, b, cc, d, rr, id);
+        if (numObstLines + r < SNB_MAX_ORCA_LINES)
+            lines[numObstLines + r] = agent_orca_line(px, py, vx, vy, radius, (float)a, (float)b, (float)cc, (float)d,
+                                                      (float)(rr + 0.01 + cfg.safety_space), 1.0f / timeHorizon, timeStep);
+        if (P.nbr) P.nbr[(size_t)(genv * H + i) * maxNeighbors + r] = id;
+    }
+    if (P.nbr) for (int r = n_nb; r < maxNeighbors; ++r) P.nbr[(size_t)(genv * H + i) * maxNeighbors + r] = -1;
+    if (overflow && P.status) atomicExch(P.status, SNB_EOVERFLOW);
+
+    float rx, ry;
+    const int lineFail = lp2_serial(lines, nLines, maxSpeed, prefx, prefy, false, rx, ry);
+    if (lineFail < nLines) {
+        Line proj[SNB_MAX_ORCA_LINES];
+        lp3_serial(lines, nLines, numObstLines, lineFail, maxSpeed, rx, ry, proj);
+    }
+    out_vx = rx; out_vy = ry;
+}
+
 // utils_plus.closest_point_on_segment (utils_plus.py:21-42)
 __device__ __forceinline__ void closest_point_on_segment(double x1, double y1, double x2, double y2, double x3, double y3,
                                                          double &ox, double &oy)
@@ -1085,6 +1297,18 @@ __global__ void __launch_bounds__(CROWD_THREADS) crowd_step_kernel(const CrowdPa
     if (aligned) mbar_wait(bar, 0);
     __syncthreads();
 
+    // ---- phase 1 (large ORCA batches): one thread per human ----
+    if (P.thread_mode) {
+        for (int task = tid; task < nA; task += blockDim.x) {
+            const int e = task / H, i = task - e * H;
+            const int genv = env0 + e;
+            if (P.active && !P.active[genv]) continue;
+            float fx, fy;
+            orca_predict_thread(P, T, e, i, genv, fx, fy);
+            T.act[2 * task] = (double)fx; T.act[2 * task + 1] = (double)fy;
+            if (!P.full_step && P.out_v) { P.out_v[2 * (goff + task)] = (double)fx; P.out_v[2 * (goff + task) + 1] = (double)fy; }
+        }
+    } else
     // ---- phase 1: one warp per human ----
     for (int task = warp; task < nA; task += nwarps) {
         const int e = task / H, i = task - e * H;
@@ -1224,6 +1448,10 @@ __global__ void __launch_bounds__(CROWD_THREADS) crowd_step_kernel(const CrowdPa
 // ---------------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------------
+/* ORCA phase 1 switches from one warp per human to one thread per human at this many humans per launch (B200, H = 10, r01:
+ * 10 240 humans: warp 53 us vs thread 84 us; 40 960: 146 vs 60 us; 2.6 M: 7.07 vs 1.59 ms) */
+#define SNB_THREAD_MODE_MIN_AGENTS 24576
+
 static int choose_epc(int H)
 {
     int epc = 48 / (H > 0 ? H : 1);
@@ -1279,7 +1507,22 @@ static int launch_crowd(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const S
         P.n_seg = obs->n_seg; P.segs = obs->d_segs;
         P.n_vert = (int)obs->verts.size(); P.verts = obs->d_verts; P.nodes = obs->d_nodes; P.bsp_root = obs->root;
     } else { P.bsp_root = -1; }
+    // one thread per human when the launch has enough humans to fill the GPU that way (SNB_CROWD_MODE=warp|thread overrides)
+    {
+        const char *m = getenv("SNB_CROWD_MODE");
+        const bool orca = cfg->policy != SNB_POLICY_SFM;
+        if (m && m[0] == 't') P.thread_mode = orca;
+        else if (m && m[0] == 'w') P.thread_mode = 0;
+        else P.thread_mode = orca && (long long)st->B * st->H >= SNB_THREAD_MODE_MIN_AGENTS;
+    }
     P.epc = choose_epc(st->H);
+    if (P.thread_mode) {                      // a CTA's 256 threads want ~256 humans: more environments per CTA
+        int epc = CROWD_THREADS / st->H;
+        if (epc < 1) epc = 1;
+        if (epc > 64) epc = 64;
+        if ((epc * st->H) & 1) epc += (epc > 1 ? -1 : 1);
+        if (((epc * st->H) & 1) == 0 && crowd_smem_bytes(epc, st->H, st->E, P.n_seg) <= 96 * 1024) P.epc = epc;
+    }
     P.full_step = full_step;
     P.n_actions = n_actions; P.next_h = next_h; P.next_robot = next_robot;
 

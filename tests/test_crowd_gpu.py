@@ -632,3 +632,31 @@ discomfort_penalty_factor = 0.5
         assert torch.equal(e2.state.rpx, next_r[:, k, 0]) and torch.equal(e2.state.rpy, next_r[:, k, 1])
     env.step(acts[:, 0].contiguous())
     env.check_status()
+
+
+@pytest.mark.parametrize("case", ["policy_1024x10", "policy_dense", "policy_ragged", "policy_single", "ties", "hallway", "bottleneck", "squeeze",
+                                  "rollout_orca", "rollout_orca_plus", "whatif_orca", "whatif_orca_plus"])
+def test_thread_per_human_orca_is_bit_identical(monkeypatch, case):
+    """The one-thread-per-human ORCA path (large batches) against the same oracle comparisons as the warp-cooperative path:
+    neighbour lists, velocities, multi-step rollouts and the what-if step stay bit-exact with SNB_CROWD_MODE=thread."""
+    monkeypatch.setenv("SNB_CROWD_MODE", "thread")
+    if case == "policy_1024x10":
+        test_orca_policy_bit_exact(1024, 10, 4.0)
+    elif case == "policy_dense":
+        test_orca_policy_bit_exact(256, 10, 1.2)
+    elif case == "policy_ragged":
+        test_orca_policy_bit_exact(33, 20, 3.0)
+    elif case == "policy_single":
+        test_orca_policy_bit_exact(1, 1, 1.0)
+    elif case == "ties":
+        test_orca_exact_ties_follow_kdtree_visit_order()
+    elif case in ("hallway", "bottleneck", "squeeze"):
+        test_orca_plus_obstacles_bit_exact(case, {"hallway": HALLWAY, "bottleneck": BOTTLENECK, "squeeze": SQUEEZE}[case])
+    elif case == "rollout_orca":
+        test_env_step_batch_rollout_vs_oracle("orca", 1024, 10, None, 40)
+    elif case == "rollout_orca_plus":
+        test_env_step_batch_rollout_vs_oracle("orca_plus", 256, 6, BOTTLENECK, 25)
+    elif case == "whatif_orca":
+        test_env_whatif_equals_step_on_a_copy("orca", 512, 10, None, 0)
+    else:
+        test_env_whatif_equals_step_on_a_copy("orca_plus", 128, 6, BOTTLENECK, 1)

@@ -1,4 +1,4 @@
-"""Times / profiles the crowd step alone: ORCA 1024 x 10 (configs[1]) and an HBM-sized batch (ncu target)."""
+"""Times the crowd step alone in both ORCA phase-1 modes (SNB_CROWD_MODE=warp|thread): configs[1] and larger batches."""
 import configparser
 import os
 import sys
@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 from bench import ENV_CFG  # noqa: E402
 from snb.env import CrowdSimPlusBatch  # noqa: E402
 
-for B in (1024, 1 << 18):
+for B in (256, 1024, 4096, 16384, 1 << 18):
     cfg = configparser.RawConfigParser()
     cfg.read_string(ENV_CFG.format(H=10))
     env = CrowdSimPlusBatch(B, "cuda")
@@ -20,11 +20,16 @@ for B in (1024, 1 << 18):
     env.freeze_done = False
     env.reset('test', test_cases=np.arange(B) % 500)
     act = torch.zeros(B, 2, dtype=torch.float64, device="cuda"); act[:, 1] = 0.5
-    for _ in range(3):
-        env.step(act)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(10):
-        env.step(act)
-    b.record(); torch.cuda.synchronize()
-    print(f"ORCA {B} x 10: {a.elapsed_time(b) / 10 * 1e3:.1f} us per step, {B / (a.elapsed_time(b) / 10 * 1e-3) / 1e6:.1f} M env-steps/s")
+    flush = torch.empty(64 * 1024 * 1024, device="cuda", dtype=torch.float32)
+    for mode in ("warp", "thread"):
+        os.environ["SNB_CROWD_MODE"] = mode
+        for _ in range(3):
+            env.step(act)
+        ts = []
+        for _ in range(8):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); env.step(act); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        t = float(np.mean(ts))
+        print(f"ORCA {B:7d} x 10  {mode:6s}: {t * 1e3:9.1f} us per step, {B / (t * 1e-3) / 1e6:7.1f} M env-steps/s")
