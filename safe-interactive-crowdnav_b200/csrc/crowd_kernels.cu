@@ -192,7 +192,7 @@ struct CrowdParams {
     int n_actions; // full_step == 2: robot_action is [B, n_actions, 2]; reward / dmin / flags are [B, n_actions]
     double *next_h;     // full_step == 2: [B, H, 4] next observable human states (px, py, vx, vy)
     double *next_robot; // full_step == 2: [B, n_actions, 2] constrained next robot position (optional)
-    int thread_mode;    // ORCA phase 1: 0 = one warp per human (small launches), 1 = one thread per human (large batches)
+    int thread_mode;    // phase 1: 0 = one warp per human (small launches), 1 = one thread per human (large batches)
 };
 
 struct Line { float px, py, dx, dy; };
@@ -1047,6 +1047,48 @@ __device__ void sfm_predict_warp(const CrowdParams &P, const Tile &T, int e, int
     else { out_vx = new_vx; out_vy = new_vy; }
 }
 
+// SFM.predict for one human by ONE thread (large batches): the reference's own sequential accumulation order
+// (social_force.py:58-80: other agents in `ob` order, then the segments).
+__device__ void sfm_predict_thread(const CrowdParams &P, const Tile &T, int e, int i, double &out_vx, double &out_vy)
+{
+    const SnbPolicyCfg &cfg = P.cfg;
+    const int H = P.st.H, E = P.st.E;
+    const int n_others = H - 1 + P.st.n_obs_extras;
+    const int k = e * H + i;
+    const double px = T.px[k], py = T.py[k], vx = T.vx[k], vy = T.vy[k], radius = T.rad[k];
+    const double gx = T.gx[k], gy = T.gy[k], v_pref = T.vpref[k];
+    double fx = 0.0, fy = 0.0;
+    for (int c = 0; c < n_others; ++c) {
+        double opx, opy, ovx, ovy, orad; int id;
+        load_other(T, H, E, e, i, c, opx, opy, ovx, ovy, orad, id);
+        const double adjustment = fabs(cfg.sfm_radius - orad) + 0.01;
+        const double dx = px - opx, dy = py - opy;
+        const double d = sqrt(dx * dx + dy * dy);
+        const double ee = cfg.A * exp((radius + orad + adjustment - d) / cfg.B);
+        fx += ee * (dx / d); fy += ee * (dy / d);
+    }
+    for (int s = 0; s < P.n_seg; ++s) {
+        const double *L = T.segs + 4 * s;
+        double As, Bs;
+        if (cfg.is_bottleneck && s >= 2) { As = cfg.A_bottleneck; Bs = cfg.B_bottleneck; } else { As = cfg.A_static; Bs = cfg.B_static; }
+        double ox, oy;
+        closest_point_on_segment(L[0], L[1], L[2], L[3], px, py, ox, oy);
+        const double dx = px - ox, dy = py - oy;
+        const double d = sqrt(dx * dx + dy * dy);
+        const double ee = As * exp((radius + 0.01 - d) / Bs);
+        fx += ee * (dx / d); fy += ee * (dy / d);
+    }
+    double ddx = gx - px, ddy = gy - py;
+    double dist_to_goal = sqrt(ddx * ddx + ddy * ddy);
+    dist_to_goal = dist_to_goal < 1e-6 ? 1.0 : dist_to_goal;
+    const double desired_vx = (ddx / dist_to_goal) * v_pref, desired_vy = (ddy / dist_to_goal) * v_pref;
+    const double cdx = cfg.KI * (desired_vx - vx), cdy = cfg.KI * (desired_vy - vy);
+    const double new_vx = vx + (cdx + fx) * cfg.time_step, new_vy = vy + (cdy + fy) * cfg.time_step;
+    const double act_norm = sqrt(fma(new_vy, new_vy, new_vx * new_vx)); // np.linalg.norm
+    if (act_norm > v_pref) { out_vx = new_vx / act_norm * v_pref; out_vy = new_vy / act_norm * v_pref; }
+    else { out_vx = new_vx; out_vy = new_vy; }
+}
+
 // ---- fp64 geometry of the clamp (numpy semantics: np.dot / np.linalg.norm fuse, see oracle/crowd_oracle.c) ----
 __device__ __forceinline__ double npdot2(double x0, double x1, double y0, double y1) { return fma(x1, y1, x0 * y0); }
 __device__ __forceinline__ double npnorm2(double x, double y) { return sqrt(fma(y, y, x * x)); }
@@ -1297,16 +1339,23 @@ __global__ void __launch_bounds__(CROWD_THREADS) crowd_step_kernel(const CrowdPa
     if (aligned) mbar_wait(bar, 0);
     __syncthreads();
 
-    // ---- phase 1 (large ORCA batches): one thread per human ----
+    // ---- phase 1 (large batches): one thread per human ----
     if (P.thread_mode) {
         for (int task = tid; task < nA; task += blockDim.x) {
             const int e = task / H, i = task - e * H;
             const int genv = env0 + e;
             if (P.active && !P.active[genv]) continue;
-            float fx, fy;
-            orca_predict_thread(P, T, e, i, genv, fx, fy);
-            T.act[2 * task] = (double)fx; T.act[2 * task + 1] = (double)fy;
-            if (!P.full_step && P.out_v) { P.out_v[2 * (goff + task)] = (double)fx; P.out_v[2 * (goff + task) + 1] = (double)fy; }
+            double ax, ay;
+            if (P.cfg.policy == SNB_POLICY_SFM) {
+                sfm_predict_thread(P, T, e, i, ax, ay);
+                if (P.nbr_cnt) P.nbr_cnt[genv * H + i] = 0;
+            } else {
+                float fx, fy;
+                orca_predict_thread(P, T, e, i, genv, fx, fy);
+                ax = (double)fx; ay = (double)fy;
+            }
+            T.act[2 * task] = ax; T.act[2 * task + 1] = ay;
+            if (!P.full_step && P.out_v) { P.out_v[2 * (goff + task)] = ax; P.out_v[2 * (goff + task) + 1] = ay; }
         }
     } else
     // ---- phase 1: one warp per human ----
@@ -1510,10 +1559,9 @@ static int launch_crowd(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const S
     // one thread per human when the launch has enough humans to fill the GPU that way (SNB_CROWD_MODE=warp|thread overrides)
     {
         const char *m = getenv("SNB_CROWD_MODE");
-        const bool orca = cfg->policy != SNB_POLICY_SFM;
-        if (m && m[0] == 't') P.thread_mode = orca;
+        if (m && m[0] == 't') P.thread_mode = 1;
         else if (m && m[0] == 'w') P.thread_mode = 0;
-        else P.thread_mode = orca && (long long)st->B * st->H >= SNB_THREAD_MODE_MIN_AGENTS;
+        else P.thread_mode = (long long)st->B * st->H >= SNB_THREAD_MODE_MIN_AGENTS;
     }
     P.epc = choose_epc(st->H);
     if (P.thread_mode) {                      // a CTA's 256 threads want ~256 humans: more environments per CTA

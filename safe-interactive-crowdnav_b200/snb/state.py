@@ -104,6 +104,7 @@ class Obstacles:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
-            _capi.lib.snb_obstacles_destroy(h)
+        lib = getattr(_capi, "lib", None)      # None while the interpreter shuts down
+        if h and lib is not None:
+            lib.snb_obstacles_destroy(h)
             self._h = None

@@ -10,6 +10,7 @@ Tolerances (stated per north_star):
     step, <= 1e-8 m over the golden episodes.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -635,10 +636,12 @@ discomfort_penalty_factor = 0.5
 
 
 @pytest.mark.parametrize("case", ["policy_1024x10", "policy_dense", "policy_ragged", "policy_single", "ties", "hallway", "bottleneck", "squeeze",
-                                  "rollout_orca", "rollout_orca_plus", "whatif_orca", "whatif_orca_plus"])
+                                  "rollout_orca", "rollout_orca_plus", "whatif_orca", "whatif_orca_plus", "sfm_4096x25", "sfm_bottleneck",
+                                  "rollout_sfm", "whatif_sfm", "sfm_reference_episodes"])
 def test_thread_per_human_orca_is_bit_identical(monkeypatch, case):
-    """The one-thread-per-human ORCA path (large batches) against the same oracle comparisons as the warp-cooperative path:
-    neighbour lists, velocities, multi-step rollouts and the what-if step stay bit-exact with SNB_CROWD_MODE=thread."""
+    """The one-thread-per-human path (large batches) against the same oracle / reference comparisons as the warp-cooperative path:
+    ORCA neighbour lists, velocities, multi-step rollouts and the what-if step stay bit-exact with SNB_CROWD_MODE=thread; SFM keeps
+    its tolerances (it now sums in the reference's sequential order)."""
     monkeypatch.setenv("SNB_CROWD_MODE", "thread")
     if case == "policy_1024x10":
         test_orca_policy_bit_exact(1024, 10, 4.0)
@@ -658,5 +661,17 @@ def test_thread_per_human_orca_is_bit_identical(monkeypatch, case):
         test_env_step_batch_rollout_vs_oracle("orca_plus", 256, 6, BOTTLENECK, 25)
     elif case == "whatif_orca":
         test_env_whatif_equals_step_on_a_copy("orca", 512, 10, None, 0)
-    else:
+    elif case == "whatif_orca_plus":
         test_env_whatif_equals_step_on_a_copy("orca_plus", 128, 6, BOTTLENECK, 1)
+    elif case == "sfm_4096x25":
+        test_sfm_policy_matches_oracle(4096, 25, HALLWAY, 0)
+    elif case == "sfm_bottleneck":
+        test_sfm_policy_matches_oracle(512, 6, BOTTLENECK, 1)
+    elif case == "rollout_sfm":
+        test_env_step_batch_rollout_vs_oracle("sfm", 1024, 25, HALLWAY, 15)
+    elif case == "whatif_sfm":
+        test_env_whatif_equals_step_on_a_copy("sfm", 256, 25, HALLWAY, 0)
+    else:
+        for path in rollout_files():
+            if "sfm" in os.path.basename(path):
+                test_env_step_replays_reference_episode(path)

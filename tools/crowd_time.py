@@ -12,9 +12,13 @@ sys.path.insert(0, ROOT)
 from bench import ENV_CFG  # noqa: E402
 from snb.env import CrowdSimPlusBatch  # noqa: E402
 
-for B in (256, 1024, 4096, 16384, 1 << 18):
+for B, H, pol, sim in ((1024, 10, "orca", "circle_crossing"), (4096, 10, "orca", "circle_crossing"), (1 << 18, 10, "orca", "circle_crossing"),
+                       (1024, 25, "sfm", "hallway"), (4096, 25, "sfm", "hallway"), (1 << 16, 25, "sfm", "hallway")):
     cfg = configparser.RawConfigParser()
-    cfg.read_string(ENV_CFG.format(H=10))
+    txt = ENV_CFG.format(H=H).replace("policy = orca", f"policy = {pol}").replace("circle_crossing", sim)
+    if sim == "hallway":
+        txt = txt.replace("rect_width = 1.75", "rect_width = 6.0").replace("rect_height = 4", "rect_height = 12")
+    cfg.read_string(txt)
     env = CrowdSimPlusBatch(B, "cuda")
     env.configure(cfg)
     env.freeze_done = False
@@ -32,4 +36,4 @@ for B in (256, 1024, 4096, 16384, 1 << 18):
             a.record(); env.step(act); b.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
         t = float(np.mean(ts))
-        print(f"ORCA {B:7d} x 10  {mode:6s}: {t * 1e3:9.1f} us per step, {B / (t * 1e-3) / 1e6:7.1f} M env-steps/s")
+        print(f"{pol:5s} {B:7d} x {H:2d}  {mode:6s}: {t * 1e3:9.1f} us per step, {B / (t * 1e-3) / 1e6:7.1f} M env-steps/s")
