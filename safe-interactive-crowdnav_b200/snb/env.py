@@ -169,12 +169,18 @@ class CrowdSimPlusBatch:
 
     # ------------------------------------------------------------------ step
     def _launch(self, action, active, stream=None, nbr=None, nbr_cnt=None):
-        pc, dc, rc = self._cfgs
-        st = self.state.cstruct()
-        _capi.check(_capi.lib.snb_env_step(C.byref(pc), C.byref(dc), C.byref(rc), C.byref(st),
+        # the argument block is rebuilt only when the state object changes (reset): a step is then one ctypes call
+        if getattr(self, "_argc_state", None) is not self.state:
+            pc, dc, rc = self._cfgs
+            self._argc = (C.byref(pc), C.byref(dc), C.byref(rc), self.state.cstruct())
+            self._argc_state = self.state
+            self._argc_tail = (_capi.ptr(self.reward), _capi.ptr(self.dmin), _capi.ptr(self.flags))
+            self._argc_status = _capi.ptr(self.status)
+        pc, dc, rc, st = self._argc
+        _capi.check(_capi.lib.snb_env_step(pc, dc, rc, C.byref(st),
                                            self.obstacles.handle if self.obstacles is not None else None,
-                                           _capi.ptr(action), _capi.ptr(active), _capi.ptr(self.reward), _capi.ptr(self.dmin),
-                                           _capi.ptr(self.flags), _capi.ptr(nbr), _capi.ptr(nbr_cnt), _capi.ptr(self.status),
+                                           _capi.ptr(action), _capi.ptr(active), *self._argc_tail,
+                                           _capi.ptr(nbr), _capi.ptr(nbr_cnt), self._argc_status,
                                            _capi.stream_ptr(stream)), "snb_env_step")
 
     def step(self, robot_action, stream=None, nbr=None, nbr_cnt=None):
@@ -184,7 +190,7 @@ class CrowdSimPlusBatch:
         if not (isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.float64 and a.is_contiguous()):
             a = torch.as_tensor(np.asarray(a, np.float64).reshape(self.B, 2)).to(self.device)
         self._launch(a, self.active if self.freeze_done else None, stream, nbr, nbr_cnt)
-        done = (self.flags & _capi.F_DONE) != 0
+        done = self.flags >= _capi.F_DONE            # F_DONE is the highest flag bit: one compare instead of and + ne
         if self.freeze_done:
             self.active &= (~done).to(torch.uint8)
         return self.reward, done, self.flags
