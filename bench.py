@@ -278,7 +278,9 @@ def run_ours(args):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 tensor-core GEMM/attention with fp32 accumulation (denoiser); f32 ORCA as in RVO2 on f64 state (crowd step)",
+            "dtype": "bf16",
+            "dtype_note": "denoiser: bf16 tensor-core GEMM / attention operands with fp32 accumulation, fp32 softmax / LayerNorm statistics / DDIM state; "
+                          "crowd step: f32 ORCA as in RVO2 on f64 state, f64 SFM",
             "data": "synthetic: seeded circle-crossing scenes (reference generator, seeds 1000+b), seeded random encoder + denoiser "
                     "weights of the reference architecture, x_T from the library's Philox generator",
             "config": {"workload": f"configs[1]+configs[3]: CrowdSimPlus ORCA step {B} envs x {H} humans + JMID {S} samples x {NS} DDIM "
