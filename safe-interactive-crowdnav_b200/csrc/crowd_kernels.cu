@@ -1280,7 +1280,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 
 #define CROWD_THREADS 256
 
-__global__ void __launch_bounds__(CROWD_THREADS) crowd_step_kernel(const CrowdParams P)
+__global__ void __launch_bounds__(CROWD_THREADS, 3) crowd_step_kernel(const CrowdParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int H = P.st.H, E = P.st.E, B = P.st.B;
