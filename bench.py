@@ -21,7 +21,12 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (os.path.join(ROOT, "safe-interactive-crowdnav_b200"), os.path.join(ROOT, "oracle")):
+sys.path.insert(0, os.path.join(ROOT, "safe-interactive-crowdnav_b200"))
+
+
+def _oracle_on_path():
+    """oracle/ is test infrastructure: only the cpu_baseline / --impl reference legs import it (never the GPU arm)."""
+    p = os.path.join(ROOT, "oracle")
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -119,14 +124,13 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def make_weights():
-    import jmid_oracle as JO
-    return JO.make_random_weights(5)
-
-
-def make_encoder_weights():
-    import predictor_oracle as PO
-    return PO.make_random_encoder_weights(9)
+def load_weights(synthetic=False):
+    """(encoder, ddpm, description): the shipped JMID checkpoint (tests/golden/ckpt_jmid_epoch121.npz, the tensor export of the
+    reference's sim_gen_sicnav_p_midjp_cvg_epoch121.pt) unless --synthetic-weights; product code only (snb.jmid.weights)."""
+    from snb.jmid import weights as W
+    if synthetic:
+        return W.synthetic_encoder(9), W.synthetic_ddpm(5), "seeded random-init weights of the JMID architecture (--synthetic-weights)"
+    return W.default_weights()
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -157,8 +161,11 @@ def run_ours(args):
     env.configure(cfg)
     env.freeze_done = False                      # steady-state throughput: every env steps every iteration
     env.reset('test', test_cases=(rank * B + np.arange(B)) % 500)
-    fc_ = ForecasterBatch(make_encoder_weights(), make_weights(), max_envs=B, H=H, num_samples=S, step_size=NS, horizon=T,
+    enc_w, ddpm_w, weights_desc = load_weights(args.synthetic_weights)
+    fc_ = ForecasterBatch(enc_w, ddpm_w, max_envs=B, H=H, num_samples=S, step_size=NS, horizon=T,
                           joint=True, dt=0.25, radius=args.attention_radius, device=dev, seed=1234 + rank)
+    if args.attention_radius != 3.0:
+        fc_.set_position_std(3.0)    # the widened radius only forces A = H; positions keep the 3.0 m scale the network was trained with
     den = fc_.denoiser
     st = env.state
     out_bufs = (torch.zeros(B, H, S, T + 1, 2, dtype=torch.float64, device=dev), torch.zeros(B, H, S, dtype=torch.float64, device=dev))
@@ -281,8 +288,8 @@ def run_ours(args):
             "dtype": "bf16",
             "dtype_note": "denoiser: bf16 tensor-core GEMM / attention operands with fp32 accumulation, fp32 softmax / LayerNorm statistics / DDIM state; "
                           "crowd step: f32 ORCA as in RVO2 on f64 state, f64 SFM",
-            "data": "synthetic: seeded circle-crossing scenes (reference generator, seeds 1000+b), seeded random encoder + denoiser "
-                    "weights of the reference architecture, x_T from the library's Philox generator",
+            "data": "synthetic: seeded circle-crossing scenes (reference generator, seeds 1000+b), x_T from the library's Philox generator; "
+                    "encoder + denoiser weights: " + weights_desc,
             "config": {"workload": f"configs[1]+configs[3]: CrowdSimPlus ORCA step {B} envs x {H} humans + JMID {S} samples x {NS} DDIM "
                                    f"iterations per env-step ({A * S * T} tokens/env, cross-sample attention), per GPU",
                        "envs_per_gpu": B, "humans": H, "samples": S, "denoise_steps": NS, "tokens_per_env": A * S * T,
@@ -290,7 +297,8 @@ def run_ours(args):
                        "context": "computed on device from the 6-frame history rings (clustering, scene graph, LSTM encoder)",
                        "attention_radius": args.attention_radius, "mean_cluster_size": mean_cluster,
                        "attention_radius_note": "default 1e6 puts all 10 humans inside the attention cluster (configs[3]: A = H = 10, the "
-                                                "full workload the metric names); the shipped 3.0 m run is reported in `faithful_3m`",
+                                                "full workload the metric names) while positions stay standardised by the shipped 3.0 m "
+                                                "(snb_pred_set_position_std); the shipped 3.0 m run is reported in `faithful_3m`",
                        "robot_policy": "Linear stand-in (MPC solve is CPU code outside the path)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": ke},
             "gpu_launches": int(launches),
@@ -431,7 +439,7 @@ def cpu_step_sample(H, S, NS, sample_envs, threads, radius):
     """The CPU restatement of the same step on a bounded sample: ORCA step of `sample_envs` envs (C oracle, pthreads) + the
     whole predict_ret_best of the same envs (numpy / torch CPU oracle: clustering, encoder, JMID denoise, integration,
     assembly) + the MPC ingest.  Returns seconds."""
-    import jmid_oracle as JO
+    _oracle_on_path()
     import oracle_lib as ol
     import predictor_oracle as PO
     torch.set_num_threads(threads)
@@ -444,7 +452,7 @@ def cpu_step_sample(H, S, NS, sample_envs, threads, radius):
     env.rpy[:] = -4.0; env.rgy[:] = 4.0
     pcfg, rcfg, door = ol.default_policy_cfg("orca"), ol.default_reward_cfg(), ol.DoorCfg(enabled=0)
     if not hasattr(cpu_step_sample, "w"):
-        cpu_step_sample.w = (make_encoder_weights(), make_weights())
+        cpu_step_sample.w = load_weights()[:2]       # the CPU arm runs the same (shipped) weights as the GPU arm
     ew, dw = cpu_step_sample.w
     g = torch.Generator().manual_seed(0)
     xT = torch.randn(sample_envs, S * H, 8, 2, generator=g)
@@ -459,7 +467,7 @@ def cpu_step_sample(H, S, NS, sample_envs, threads, radius):
             pos = cur + vel[b] * tt[0]
             hist = np.concatenate([pos[1:], np.zeros((H, 6, 1))], -1); rob = np.concatenate([pos[0], np.zeros((6, 1))], -1)
             A = len(PO.encoder_inputs(hist, rob, 0.25, radius)["ped_ids"])
-            fc, lw, _ = PO.predict_ret_best(ew, dw, hist, rob, xT[b, :S * A], S, S, NS, radius=radius)
+            fc, lw, _ = PO.predict_ret_best(ew, dw, hist, rob, xT[b, :S * A], S, S, NS, radius=radius, pos_std=3.0)
             PO.mpc_ingest(fc, lw, dt=0.25, horiz=4, joint=True)
     return time.perf_counter() - t0
 
@@ -522,6 +530,7 @@ if __name__ == "__main__":
     ap.add_argument("--denoise-steps", type=int, default=20)
     ap.add_argument("--cpu-sample-envs", type=int, default=12, help="envs of the workload the CPU port steps per sample (~1 s each on 16 cores)")
     ap.add_argument("--skip-sim-only", action="store_true", help="skip the crowd-step-only / reset / what-if side measurements")
+    ap.add_argument("--synthetic-weights", action="store_true", help="seeded random-init weights instead of the shipped checkpoint")
     ap.add_argument("--attention-radius", type=float, default=1e6,
                     help="attention / cluster radius of the predictor; 1e6 = every human inside the cluster (A = H, the metric's workload), "
                          "3.0 = the shipped value")

@@ -145,7 +145,8 @@ int snb_policy_step(const SnbPolicyCfg *cfg, const SnbCrowdState *state, const S
  * clamp (constrain_agent_action_exact, crowd_sim_plus.py:869-989), robot clamp + wall flag, robot-human
  * collision scan, frozen / goal / time-out, reward, state integration (Agent.step agent_plus.py:199-214,
  * Human.step human_plus.py:118-120), clocks and human arrival times.  State is updated in place.
- * robot_action_dev [B*2] = (vx,vy) or (v,r).  active_dev (optional uint8[B]): environments with 0 are skipped.
+ * robot_action_dev [B*2] = (vx,vy) or (v,r).  active_dev (optional uint8[B]): environments with 0 are skipped (state untouched)
+ * and their reward / flags outputs are written as 0.
  * Outputs (each optional): reward_dev[B], dmin_dev[B], flags_dev[B] (SNB_F_*), nbr_dev / nbr_cnt_dev as above.
  */
 int snb_env_step(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const SnbRewardCfg *reward_cfg,
@@ -291,6 +292,12 @@ int snb_pred_set_history(SnbPredictor *p, const double *hist_dev, const double *
 int snb_pred_encode(SnbPredictor *p, int32_t B, double radius, double dt, float *ctx_dev, int32_t *n_in_dev,
                     int32_t *ped_ids_dev, uint8_t *in_cluster_dev, void *stream);
 
+/* The reference standardises positions by the attention radius (std[0:2] = attention_radius, preprocessing.py:477-478, 540), and
+ * that is what snb_pred_encode / snb_pred_predict do with their `radius` argument.  A benchmark that widens `radius` only to force
+ * every human into the cluster (configs[3]: A = H) can pin the position scale the network was trained with (3.0) here;
+ * pos_std = 0 restores the reference behaviour. */
+int snb_pred_set_position_std(SnbPredictor *p, double pos_std);
+
 /* standard-normal noise (Philox4x32-10 + Box-Muller), element i a function of (seed, offset, i) only */
 int snb_pred_noise(float *out_dev, int64_t n, uint64_t seed, uint64_t offset, void *stream);
 
@@ -324,6 +331,29 @@ int snb_pred_kde_topk(const float *pos_dev, int32_t B, int32_t S, int32_t A, int
 int snb_pred_ingest(const double *forecasts_dev, const double *logw_dev, int32_t B, int32_t H, int32_t k, int32_t T,
                     int32_t horiz, double dt, int32_t joint, double *resh_dev, double *weights_dev, double *goals_dev,
                     double *vpref_dev, void *stream);
+
+/* What SICNavAcados.predict hands the solver after the ingest (sicnav_diffusion/policy/sicnav_acados.py), batched over B envs:
+ *   mpc_state_dev [B, 10 + nX_hums] = convert_to_mpc_state_vector (:222-289) of the joint state built at :1655-1681:
+ *       px, py, sin(theta), cos(theta), v, omega, v_dot, omega_dot, gx, gy | per human px, py, vx, vy, gx, gy (+ k log-weights when
+ *       joint = 0, iMID) | k log-weights (joint = 1, JMID);  nX_hums = 6 H + k (joint) or (6 + k) H.
+ *       robot_dev [B,9] = px, py, theta, lvel, omega, v_dot, omega_dot, gx, gy;  humans_dev [B,H,4] = px, py, vx, vy;
+ *       goals_dev [B,H,2], weights_dev as written by snb_pred_ingest.  human_theta_dev [B,H] (optional) = atan2(vy, vx), 0 at rest (:1678).
+ *   stage_params_dev [B, horiz+1, n_prefix + 4 H k + n_static] = the per-stage vector of :1389-1413:
+ *       prefix (x_ref, u_ref, Q, R, Q_T: MPC-side, stage_prefix_dev [B, horiz+1, n_prefix]) | X_t[:,0] | X_t[:,1] | X_t+1[:,0] | X_t+1[:,1]
+ *       (X = resh_dev [B, horiz+1, H k, 2] of snb_pred_ingest; stage horiz reuses t = horiz - 1, :1403-1405) | static_obs_dev [n_static].
+ * mpc_state_dev / stage_params_dev may each be NULL. */
+int snb_pred_mpc_pack(const double *robot_dev, const double *humans_dev, const double *goals_dev, const double *weights_dev,
+                      const double *resh_dev, const double *stage_prefix_dev, const double *static_obs_dev, int32_t B, int32_t H,
+                      int32_t k, int32_t T, int32_t horiz, int32_t joint, int32_t n_prefix, int32_t n_static, double *mpc_state_dev,
+                      double *human_theta_dev, double *stage_params_dev, void *stream);
+
+/* History bootstrap of reset_scenario_values (sicnav_acados.py:1163-1182): the forecaster is re-created and fed
+ * env.states[-past_num_frames-1 : -1] (the newest logged state is skipped; stamps are dt apart).
+ *   snb_env_log_push: CrowdSimPlus.step's `self.states.append` (crowd_sim_plus.py:1175-1181) -- writes the positions of `state`
+ *       (humans + robot, BEFORE the step) into slot `slot` of log_dev [B, L, H+1, 2] (entry H = robot);
+ *   snb_pred_bootstrap_history: fills the predictor's rings from the L-deep log whose newest slot is `newest`. */
+int snb_env_log_push(const SnbCrowdState *state, double *log_dev, int32_t L, int32_t slot, void *stream);
+int snb_pred_bootstrap_history(SnbPredictor *p, const double *log_dev, int32_t L, int32_t newest, int32_t B, void *stream);
 
 #ifdef __cplusplus
 }

@@ -365,87 +365,108 @@ if __name__ == "__main__":
 
 
 # ------------------------------------------------------------------ full predictor (a13-a17, a22-a25)
+class _S:
+    def __init__(self, x, y):
+        self.position = (x, y)
+
+
+def _pred_setup():
+    import ref_predictor_shims as RPS
+    EasyDict = RPS.install()
+    from sicnav_diffusion.JMID import mid_sim_wrapper as W
+    return EasyDict, W
+
+
+def _pred_build(EasyDict, W, H, num_draw, num_ret, step):
+    import yaml
+    REF = ref_shims.REF
+    cfg = configparser.RawConfigParser()
+    cfg.read(REF_CFG)
+    cfg.set("sim", "human_num", str(H))
+    cfg.set("human_trajectory_forecaster", "num_samples", str(num_ret))
+    y = yaml.safe_load(open(os.path.join(REF, "sicnav_diffusion/JMID/test_time_configs/mid_jp.yaml")))
+    y.update(device="cpu", model_path=os.path.join(REF, y["model_path"]), num_samples=num_draw, step_size=step)
+    return W.HumanTrajectoryForecasterSim(cfg, EasyDict(y))
+
+
+def _pred_run(out, tag, f, H, rng, spread, synthetic, eps_at=()):
+    """Feeds 8 frames of seeded quadratic motion, hooks the sampler to record ctx / x_T (and the raw sampled velocities), runs
+    predict_ret_best.  eps_at: diffusion steps t at which the reference noise net is also evaluated on (x_T, ctx)."""
+    import jmid_oracle as JO
+    import predictor_oracle as PO
+    if synthetic:
+        ew = PO.make_random_encoder_weights(seed=9)
+        md = f.mid_model.registrar.model_dict
+        with torch.no_grad():
+            for k, v in ew.items():
+                mod, pname = k.rsplit("/", 1)
+                dict(md[mod].named_parameters())[pname].copy_(v)
+            dw = JO.make_random_weights(5)
+            sd = f.mid_model.model.vel_predictor.state_dict()
+            for k, v in dw.items():
+                sd[k].copy_(v)
+    p0 = rng.uniform(-spread, spread, (H, 2)); v0 = rng.uniform(-0.8, 0.8, (H, 2))
+    rp = np.array([0.0, -spread * 0.6]); rv = np.array([0.1, 0.9])
+    acc = rng.uniform(-0.3, 0.3, (H, 2))
+    for i in range(H):
+        f.prev_states[i].clear()
+    f.prev_robot_states.clear()
+    for k in range(8):          # more than 6 frames: the ring keeps the last 6
+        t = 0.25 * k
+        f.update_state_hists(_S(*(rp + rv * t)), [_S(*(p0[i] + v0[i] * t + 0.5 * acc[i] * t * t)) for i in range(H)], t)
+    rec = {}
+    vp = f.mid_model.model.vel_predictor
+    orig_sample = vp.sample_sicnav_inference
+    orig_randn = torch.randn
+
+    def sample_hook(num_points, context, sample, bestof, **kw):
+        rec["ctx"] = context.detach().clone()
+        g = torch.Generator().manual_seed(4321)
+
+        def fake_randn(*size, **k2):
+            size = size[0] if len(size) == 1 and isinstance(size[0], (list, tuple, torch.Size)) else size
+            t_ = orig_randn(*size, generator=g)
+            if "xT" not in rec:
+                rec["xT"] = t_.clone()
+            return t_
+        torch.randn = fake_randn
+        try:
+            r = orig_sample(num_points, context, sample, bestof, **kw)
+            rec["vel"] = r[0].detach().clone()
+            return r
+        finally:
+            torch.randn = orig_randn
+    vp.sample_sicnav_inference = sample_hook
+    env_, poses, ids_in, ids_out, cv = f.convert_to_mid_state_env(f.prev_states, f.prev_robot_states)
+    fc, lw = f.predict_ret_best()
+    vp.sample_sicnav_inference = orig_sample
+    out[f"{tag}_hist"] = np.array([s_ for s_ in f.prev_states], np.float64)          # [H,6,3]
+    out[f"{tag}_robot_hist"] = np.array(f.prev_robot_states[-6:], np.float64)       # [6,3]
+    out[f"{tag}_ids_in"] = np.array(ids_in, np.int64); out[f"{tag}_ids_out"] = np.array(ids_out, np.int64)
+    out[f"{tag}_ctx"] = rec["ctx"].numpy(); out[f"{tag}_xT"] = rec["xT"].numpy()
+    out[f"{tag}_forecasts"] = fc; out[f"{tag}_logw"] = lw
+    out[f"{tag}_cfg"] = np.array([H, f.mid_model.num_samples, f.num_ret_samples, f.mid_model.config.step_size])
+    if eps_at:
+        S = f.mid_model.num_samples
+        out[f"{tag}_vel"] = rec["vel"].numpy()                                      # [S,A,T,2] raw sampled velocities
+        ctx_rep = rec["ctx"].repeat(S, 1)
+        for t in eps_at:
+            e = vp.net([rec["xT"], ctx_rep], beta=vp.var_sched.betas[[t] * ctx_rep.shape[0]])
+            out[f"{tag}_eps{t}"] = e.numpy()
+    print(f"predictor {tag}: H={H} in={list(ids_in)} out={list(ids_out)} ctx={tuple(rec['ctx'].shape)} fc={fc.shape}")
+
+
 def gen_predictor():
     """Runs the reference's own HumanTrajectoryForecasterSim (mid_sim_wrapper.py) on CPU with (a) the shipped JMID
     checkpoint and (b) seeded synthetic encoder + denoiser weights written INTO the reference modules, recording the
     histories, the cluster split, the encoder context, the injected noise and predict_ret_best's outputs."""
-    import yaml
-    import ref_predictor_shims as RPS
-    import jmid_oracle as JO
     import predictor_oracle as PO
-    EasyDict = RPS.install()
-    from sicnav_diffusion.JMID import mid_sim_wrapper as W
-    REF = ref_shims.REF
+    EasyDict, W = _pred_setup()
     cwd = os.getcwd()
-    os.chdir(REF)
+    os.chdir(ref_shims.REF)
     out = {}
-
-    class S:
-        def __init__(self, x, y):
-            self.position = (x, y)
-
-    def build(H, num_draw, num_ret, step):
-        cfg = configparser.RawConfigParser()
-        cfg.read(REF_CFG)
-        cfg.set("sim", "human_num", str(H))
-        cfg.set("human_trajectory_forecaster", "num_samples", str(num_ret))
-        y = yaml.safe_load(open(os.path.join(REF, "sicnav_diffusion/JMID/test_time_configs/mid_jp.yaml")))
-        y.update(device="cpu", model_path=os.path.join(REF, y["model_path"]), num_samples=num_draw, step_size=step)
-        return W.HumanTrajectoryForecasterSim(cfg, EasyDict(y))
-
-    def run(tag, f, H, rng, spread, synthetic):
-        if synthetic:
-            ew = PO.make_random_encoder_weights(seed=9)
-            md = f.mid_model.registrar.model_dict
-            with torch.no_grad():
-                for k, v in ew.items():
-                    mod, pname = k.rsplit("/", 1)
-                    dict(md[mod].named_parameters())[pname].copy_(v)
-                dw = JO.make_random_weights(5)
-                sd = f.mid_model.model.vel_predictor.state_dict()
-                for k, v in dw.items():
-                    sd[k].copy_(v)
-        p0 = rng.uniform(-spread, spread, (H, 2)); v0 = rng.uniform(-0.8, 0.8, (H, 2))
-        rp = np.array([0.0, -spread * 0.6]); rv = np.array([0.1, 0.9])
-        acc = rng.uniform(-0.3, 0.3, (H, 2))
-        for i in range(H):
-            f.prev_states[i].clear()
-        f.prev_robot_states.clear()
-        for k in range(8):          # more than 6 frames: the ring keeps the last 6
-            t = 0.25 * k
-            f.update_state_hists(S(*(rp + rv * t)), [S(*(p0[i] + v0[i] * t + 0.5 * acc[i] * t * t)) for i in range(H)], t)
-        rec = {}
-        vp = f.mid_model.model.vel_predictor
-        orig_sample = vp.sample_sicnav_inference
-        orig_randn = torch.randn
-
-        def sample_hook(num_points, context, sample, bestof, **kw):
-            rec["ctx"] = context.detach().clone()
-            g = torch.Generator().manual_seed(4321)
-
-            def fake_randn(*size, **k2):
-                size = size[0] if len(size) == 1 and isinstance(size[0], (list, tuple, torch.Size)) else size
-                t_ = orig_randn(*size, generator=g)
-                if "xT" not in rec:
-                    rec["xT"] = t_.clone()
-                return t_
-            torch.randn = fake_randn
-            try:
-                return orig_sample(num_points, context, sample, bestof, **kw)
-            finally:
-                torch.randn = orig_randn
-        vp.sample_sicnav_inference = sample_hook
-        env_, poses, ids_in, ids_out, cv = f.convert_to_mid_state_env(f.prev_states, f.prev_robot_states)
-        fc, lw = f.predict_ret_best()
-        vp.sample_sicnav_inference = orig_sample
-        out[f"{tag}_hist"] = np.array([s_ for s_ in f.prev_states], np.float64)          # [H,6,3]
-        out[f"{tag}_robot_hist"] = np.array(f.prev_robot_states[-6:], np.float64)       # [6,3]
-        out[f"{tag}_ids_in"] = np.array(ids_in, np.int64); out[f"{tag}_ids_out"] = np.array(ids_out, np.int64)
-        out[f"{tag}_ctx"] = rec["ctx"].numpy(); out[f"{tag}_xT"] = rec["xT"].numpy()
-        out[f"{tag}_forecasts"] = fc; out[f"{tag}_logw"] = lw
-        out[f"{tag}_cfg"] = np.array([H, f.mid_model.num_samples, f.num_ret_samples, f.mid_model.config.step_size])
-        print(f"predictor {tag}: H={H} in={list(ids_in)} out={list(ids_out)} ctx={tuple(rec['ctx'].shape)} fc={fc.shape}")
-
+    build = lambda *a: _pred_build(EasyDict, W, *a)
+    run = lambda *a: _pred_run(out, *a)
     with torch.no_grad():
         rng = np.random.default_rng(2024)
         f = build(5, 20, 20, 20)
@@ -466,6 +487,43 @@ def gen_predictor():
     np.savez_compressed(os.path.join(OUT, "predictor_cases.npz"), enc_seed=9, ddpm_seed=5, **out)
 
 
+def gen_ckpt():
+    """The SHIPPED JMID checkpoint (sim_gen_sicnav_p_midjp_cvg_epoch121.pt) for the GPU box:
+      tests/golden/ckpt_jmid_epoch121.npz   its tensors ("ddpm/<state_dict key>", "enc/<module>/<param>"; the reference tree and
+                                            its pickled nn.Modules do not travel), loadable by snb.jmid.load_checkpoint;
+      tests/golden/ckpt_c4_cases.npz        outputs of the reference's own HumanTrajectoryForecasterSim / DiffusionTraj with that
+                                            checkpoint at the C4 per-env shape (10 humans, 20 samples, 20 DDIM iterations, injected
+                                            x_T): eps at t = 100 / 55 / 5, the sampled velocities, predict_ret_best."""
+    EasyDict, W = _pred_setup()
+    cwd = os.getcwd()
+    os.chdir(ref_shims.REF)
+    out = {}
+    with torch.no_grad():
+        rng = np.random.default_rng(777)
+        f = _pred_build(EasyDict, W, 10, 20, 20, 20)
+        wts = {}
+        used_enc = ("PEDESTRIAN/node_history_encoder", "PEDESTRIAN->PEDESTRIAN/edge_encoder", "PEDESTRIAN->JRDB_ROBOT/edge_encoder",
+                    "PEDESTRIAN/edge_influence_encoder")   # the modules get_latent touches (mgcvae.py:505-880); the rest is training-only
+        for mod_name, mod in f.mid_model.registrar.model_dict.items():
+            if mod_name in used_enc:
+                for pname, t in mod.named_parameters():
+                    wts[f"enc/{mod_name}/{pname}"] = t.detach().numpy().copy()
+        for k, v in f.mid_model.model.vel_predictor.state_dict().items():
+            if k.startswith("net.layer."):     # the template layer nn.TransformerEncoder deep-copied (diffusion.py:161-166); never run
+                continue
+            wts["ddpm/" + k] = v.detach().numpy().copy()
+        np.savez(os.path.join(OUT, "ckpt_jmid_epoch121.npz"), **wts)
+        _pred_run(out, "ckpt_h10_dense", f, 10, rng, 1.0, False, eps_at=(100, 55, 5))   # every human inside one cluster
+        _pred_run(out, "ckpt_h10", f, 10, rng, 2.5, False, eps_at=(55,))
+        f = _pred_build(EasyDict, W, 3, 100, 15, 2)      # the shipped simulation setting: 100 drawn, 2 DDIM iterations, 15 kept
+        _pred_run(out, "ckpt_h3_shipped", f, 3, rng, 1.2, False, eps_at=(100,))
+    os.chdir(cwd)
+    np.savez_compressed(os.path.join(OUT, "ckpt_c4_cases.npz"), **out)
+
+
 if "predictor" in sys.argv[1:]:
     with np.errstate(all="ignore"):
         gen_predictor()
+if "ckpt" in sys.argv[1:]:
+    with np.errstate(all="ignore"):
+        gen_ckpt()

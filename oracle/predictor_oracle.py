@@ -27,7 +27,7 @@ ENC_KEYS = {
     "PEDESTRIAN->PEDESTRIAN/edge_encoder": 12,
     "PEDESTRIAN->JRDB_ROBOT/edge_encoder": 12,
 }
-STD = np.array([3.0, 3.0, 2.0, 2.0, 1.0, 1.0])   # position std is replaced by the attention radius (preprocessing.py:477-478)
+STD = np.array([3.0, 3.0, 2.0, 2.0, 1.0, 1.0])   # position std := the attention radius, 3.0 m as shipped (preprocessing.py:477-478)
 
 
 def make_random_encoder_weights(seed=9):
@@ -86,10 +86,12 @@ def edge_scaling(pos3, is_ped, radius=3.0):
     return new_edges        # removal filter [1, 0] leaves the current frame unchanged
 
 
-def encoder_inputs(hist, robot_hist, dt=0.25, radius=3.0):
+def encoder_inputs(hist, robot_hist, dt=0.25, radius=3.0, pos_std=None):
     """Everything up to the encoder: returns dict(in_cluster [H] bool, ped_ids (in-cluster humans, ascending),
     x_st [A,6,6], nb_ped [A,6,6], nb_rob [A,6,6], edge_mask [A], p0 [A,2], cv {h: [T,2]} filled by the caller)."""
     H, Th, _ = hist.shape
+    std = STD.copy()
+    std[0:2] = radius if pos_std is None else pos_std        # std[0:2] = env.attention_radius[...] (preprocessing.py:478, 540)
     inc = cluster_split(hist, robot_hist, radius)
     nodes = [i for i in range(H + 1) if inc[i]]             # 0 = robot
     states = {}
@@ -105,13 +107,13 @@ def encoder_inputs(hist, robot_hist, dt=0.25, radius=3.0):
             continue
         x = states[i]
         rel = np.zeros(6); rel[0:2] = x[-1, 0:2]
-        x_st.append((x - rel) / STD)
+        x_st.append((x - rel) / std)
         conn = es[a] > 1e-2                                   # SceneGraph.get_connection_mask
         sp, sr = np.zeros((Th, 6)), np.zeros((Th, 6))
         for b_, j in enumerate(nodes):
             if not conn[b_]:
                 continue
-            nst = (states[j] - x[-1][None, :]) / STD         # relative to the node's CURRENT full state (:541-551)
+            nst = (states[j] - x[-1][None, :]) / std         # relative to the node's CURRENT full state (:541-551)
             if j == 0:
                 sr += nst
             else:
@@ -186,11 +188,12 @@ def most_likely_samples(forecasts, k):
     return forecasts[top].permute(1, 0, 2, 3), lw.unsqueeze(0).expand(A, k)
 
 
-def predict_ret_best(enc_w, ddpm_w, hist, robot_hist, x_T, num_draw, num_ret, step, dt=0.25, horizon=8, joint=True, radius=3.0):
+def predict_ret_best(enc_w, ddpm_w, hist, robot_hist, x_T, num_draw, num_ret, step, dt=0.25, horizon=8, joint=True, radius=3.0,
+                     pos_std=None):
     """HumanTrajectoryForecasterSim.predict_ret_best (mid_sim_wrapper.py:482-509) with injected noise x_T [S*A,T,2].
     Returns (forecasts [H,k,T+1,2] float64, logw [H,k] float64, ctx [A,256])."""
     H = hist.shape[0]
-    inp = encoder_inputs(hist, robot_hist, dt, radius)
+    inp = encoder_inputs(hist, robot_hist, dt, radius, pos_std)
     ctx = encode(enc_w, inp)
     vel = JO.sample(ddpm_w, ctx, x_T, step=step, joint=joint)                       # [S,A,T,2]
     pos = JO.integrate(vel, torch.tensor(inp["p0"], dtype=torch.float32), dt)       # ascending human id == sort by node id

@@ -1399,8 +1399,12 @@ __global__ void __launch_bounds__(CROWD_THREADS, 3) crowd_step_kernel(const Crow
     for (int ea = tid; ea < nenv * nact; ea += blockDim.x) {
         const int e = ea / nact, a = ea - e * nact;
         const int genv = env0 + e;
-        if (P.active && !P.active[genv]) continue;
         const size_t oidx = (size_t)genv * nact + a;
+        if (P.active && !P.active[genv]) {
+            // a frozen environment reports nothing: its terminal reward / flags were returned by the step that finished it
+            if (P.full_step == 1) { if (P.reward) P.reward[oidx] = 0.0; if (P.flags) P.flags[oidx] = 0; }
+            continue;
+        }
         const double rpx = T.ex_px[e * E], rpy = T.ex_py[e * E], rrad = T.ex_rad[e * E];
         const double rtheta = P.st.rtheta[genv];
         const double ra0 = P.robot_action[2 * oidx], ra1 = P.robot_action[2 * oidx + 1];

@@ -275,6 +275,10 @@ extern "C" int snb_jmid_denoise_agents(SnbJmid *h, const float *ctx, const float
     SNB_REQUIRE(A >= 1 && A <= h->A, SNB_EINVAL, "snb_jmid_denoise: A=%d outside [1, %d] (the handle's agent capacity)", A, h->A);
     cudaStream_t s = (cudaStream_t)stream;
     const int stride = 100 / n_steps;
+    // t = 100, 100 - stride, ... must land on 0: the reference returns traj[0] and raises KeyError otherwise (diffusion.py:507-537)
+    SNB_REQUIRE(100 % stride == 0, SNB_EINVAL,
+                "snb_jmid_denoise: step_size=%d gives stride int(100/%d)=%d, which does not divide the 100 diffusion steps "
+                "(the reference raises KeyError: 0 on traj[0])", n_steps, n_steps, stride);
     const int n_iter = (100 + stride - 1) / stride;
     const int N = A * h->S * h->T;
     // a chunk is bounded by ROWS (chunk_envs * tokens at full A): fewer agents per env -> more envs per chunk

@@ -23,6 +23,7 @@ struct SnbPredictor {
     double *logw_env = nullptr;
     int32_t *h_n_in = nullptr, *h_order = nullptr; // pinned
     uint64_t calls = 0;
+    double pos_std = 0.0; // 0: the attention radius, as the reference (preprocessing.py:477-478)
     cudaStream_t own_stream = nullptr;
     double *d_fc = nullptr, *d_lw = nullptr; // host-call staging
     size_t d_fc_elems = 0;
@@ -57,7 +58,7 @@ int make_lstm(SnbPredictor *p, PredLstmDev *dst, const SnbLstmWeights *w, int di
 
 int run_encode(SnbPredictor *p, int B, double radius, double dt, cudaStream_t s)
 {
-    int rc = snb_k_pred_prep(p->hist, p->robot_hist, B, p->H, radius, dt, p->T, &p->prep, s);
+    int rc = snb_k_pred_prep(p->hist, p->robot_hist, B, p->H, radius, p->pos_std > 0.0 ? p->pos_std : radius, dt, p->T, &p->prep, s);
     if (rc) return rc;
     return snb_k_pred_encode(&p->enc, p->prep.x_st, p->prep.nb_ped, p->prep.nb_rob, p->prep.edge_mask, p->ctx, B * p->H, s);
 }
@@ -128,6 +129,13 @@ extern "C" int snb_pred_destroy(SnbPredictor *p)
     return SNB_OK;
 }
 
+extern "C" int snb_pred_set_position_std(SnbPredictor *p, double pos_std)
+{
+    SNB_REQUIRE(p && pos_std >= 0.0, SNB_EINVAL, "snb_pred_set_position_std: bad argument");
+    p->pos_std = pos_std;
+    return SNB_OK;
+}
+
 extern "C" int snb_pred_push_history(SnbPredictor *p, const double *hpx, const double *hpy, const double *rpx, const double *rpy, int32_t B,
                                      void *stream)
 {
@@ -188,6 +196,8 @@ extern "C" int snb_pred_predict(SnbPredictor *p, int32_t B, const float *noise, 
     SNB_REQUIRE(num_ret >= 1 && num_ret <= p->S, SNB_EINVAL, "snb_pred_predict: num_ret=%d outside [1, S=%d]", num_ret, p->S);
     SNB_REQUIRE(p->n_pushed > 0, SNB_EINVAL, "snb_pred_predict: no history (push or set the rings first)");
     SNB_REQUIRE(radius > 0.0 && dt > 0.0, SNB_EINVAL, "snb_pred_predict: radius and dt must be positive");
+    SNB_REQUIRE(n_steps >= 1 && n_steps <= 100 && 100 % (100 / n_steps) == 0, SNB_EINVAL,
+                "snb_pred_predict: step_size=%d: int(100/step_size) must divide 100 (diffusion.py:507-537)", n_steps);
     if (B == 0) return SNB_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const int H = p->H, S = p->S, T = p->T;
@@ -265,6 +275,46 @@ extern "C" int snb_pred_ingest(const double *forecasts, const double *logw, int3
     SNB_REQUIRE(forecasts && logw && resh && weights && goals && vpref, SNB_EINVAL, "snb_pred_ingest: NULL argument");
     SNB_REQUIRE(B >= 0 && H >= 1 && k >= 1 && T >= 2 && horiz >= 0 && dt > 0.0, SNB_EINVAL, "snb_pred_ingest: bad sizes");
     return snb_k_pred_ingest(forecasts, logw, B, H, k, T, horiz, dt, joint, resh, weights, goals, vpref, (cudaStream_t)stream);
+}
+
+extern "C" int snb_pred_mpc_pack(const double *robot, const double *humans, const double *goals, const double *weights, const double *resh,
+                                 const double *stage_prefix, const double *static_obs, int32_t B, int32_t H, int32_t k, int32_t T,
+                                 int32_t horiz, int32_t joint, int32_t n_prefix, int32_t n_static, double *mpc_state, double *human_theta,
+                                 double *stage_params, void *stream)
+{
+    SNB_REQUIRE(robot && humans && goals && weights, SNB_EINVAL, "snb_pred_mpc_pack: NULL argument");
+    SNB_REQUIRE(B >= 0 && H >= 1 && k >= 1 && horiz >= 1 && n_prefix >= 0 && n_static >= 0, SNB_EINVAL, "snb_pred_mpc_pack: bad sizes");
+    SNB_REQUIRE(n_prefix == 0 || stage_prefix, SNB_EINVAL, "snb_pred_mpc_pack: n_prefix > 0 without stage_prefix");
+    SNB_REQUIRE(n_static == 0 || static_obs, SNB_EINVAL, "snb_pred_mpc_pack: n_static > 0 without static_obs");
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = SNB_OK;
+    if (mpc_state) rc = snb_k_pred_mpc_state(robot, humans, goals, weights, B, H, k, joint, mpc_state, human_theta, s);
+    if (!rc && stage_params) {
+        SNB_REQUIRE(resh, SNB_EINVAL, "snb_pred_mpc_pack: stage_params needs the reshaped forecasts");
+        // MID_samples[idx + 1] for idx = horiz - 1 must exist: forecasts_reshaped keeps min(T, horiz + 1) frames (:1651)
+        SNB_REQUIRE(horiz + 1 <= T, SNB_EINVAL, "snb_pred_mpc_pack: horiz + 1 = %d frames needed, the forecasts hold T = %d", horiz + 1, T);
+        rc = snb_k_pred_stage_params(resh, stage_prefix, static_obs, B, horiz, horiz + 1, H * k, n_prefix, n_static, stage_params, s);
+    }
+    return rc;
+}
+
+extern "C" int snb_env_log_push(const SnbCrowdState *st, double *log_dev, int32_t L, int32_t slot, void *stream)
+{
+    SNB_REQUIRE(st && log_dev, SNB_EINVAL, "snb_env_log_push: NULL argument");
+    SNB_REQUIRE(L >= 1 && slot >= 0 && slot < L && st->E >= 1, SNB_EINVAL, "snb_env_log_push: bad ring slot / no robot");
+    SNB_REQUIRE(st->E == 1, SNB_EINVAL, "snb_env_log_push: the simulator state has exactly one extra (the robot)");
+    return snb_k_state_log_push(st->px, st->py, st->ex_px, st->ex_py, st->B, st->H, L, slot, log_dev, (cudaStream_t)stream);
+}
+
+extern "C" int snb_pred_bootstrap_history(SnbPredictor *p, const double *log_dev, int32_t L, int32_t newest, int32_t B, void *stream)
+{
+    SNB_REQUIRE(p && log_dev, SNB_EINVAL, "snb_pred_bootstrap_history: NULL argument");
+    SNB_REQUIRE(B >= 0 && B <= p->max_envs, SNB_EINVAL, "snb_pred_bootstrap_history: B=%d beyond max_envs=%d", B, p->max_envs);
+    SNB_REQUIRE(L >= SNB_PRED_TH + 1 && newest >= 0 && newest < L, SNB_EINVAL,
+                "snb_pred_bootstrap_history: the log must hold past_num_frames + 1 = %d states (IndexError in the reference)", SNB_PRED_TH + 1);
+    int rc = snb_k_pred_bootstrap(log_dev, B, p->H, L, newest, p->hist, p->robot_hist, (cudaStream_t)stream);
+    if (!rc) p->n_pushed = SNB_PRED_TH;
+    return rc;
 }
 
 extern "C" int snb_pred_kde_topk(const float *pos, int32_t B, int32_t S, int32_t A, int32_t T, int32_t k, int32_t *sel, double *logw,

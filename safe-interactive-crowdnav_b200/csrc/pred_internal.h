@@ -22,8 +22,15 @@ struct PredPrepOut {
     double *cv;          // [B,H,horizon,2] constant-velocity forecast of every human
     double *cur;         // [B,H,2]    current position (fp64)
 };
-int snb_k_pred_prep(const double *hist, const double *robot_hist, int B, int H, double radius, double dt, int horizon,
+int snb_k_pred_prep(const double *hist, const double *robot_hist, int B, int H, double radius, double pos_std, double dt, int horizon,
                     const PredPrepOut *out, cudaStream_t s);
+int snb_k_pred_mpc_state(const double *robot, const double *humans, const double *goals, const double *weights, int B, int H, int k,
+                         int joint, double *out, double *theta, cudaStream_t s);
+int snb_k_pred_stage_params(const double *resh, const double *prefix, const double *stat, int B, int horiz, int Tp, int HK, int n_prefix,
+                            int n_stat, double *out, cudaStream_t s);
+int snb_k_state_log_push(const double *hpx, const double *hpy, const double *rpx, const double *rpy, int B, int H, int L, int slot,
+                         double *log, cudaStream_t s);
+int snb_k_pred_bootstrap(const double *log, int B, int H, int L, int newest, double *hist, double *robot_hist, cudaStream_t s);
 int snb_k_pred_push(double *hist, double *robot_hist, const double *hpx, const double *hpy, const double *rpx, const double *rpy,
                     int B, int H, int first, cudaStream_t s);
 

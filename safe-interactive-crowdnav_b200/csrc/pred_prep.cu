@@ -34,7 +34,7 @@ __device__ __forceinline__ void node_states(const double *px, const double *py, 
 }
 
 __global__ void __launch_bounds__(32 * ENVS_PER_CTA)
-pred_prep_kernel(const double *__restrict__ hist, const double *__restrict__ robot_hist, int B, int H, double radius, double dt,
+pred_prep_kernel(const double *__restrict__ hist, const double *__restrict__ robot_hist, int B, int H, double radius, double pos_std, double dt,
                  int horizon, PredPrepOut o)
 {
     __shared__ double s_st[ENVS_PER_CTA][32][TH][6];
@@ -99,7 +99,7 @@ pred_prep_kernel(const double *__restrict__ hist, const double *__restrict__ rob
         o.cur[(slot0 + h) * 2 + 0] = x;
         o.cur[(slot0 + h) * 2 + 1] = y;
     }
-    const double stdv[6] = {3.0, 3.0, 2.0, 2.0, 1.0, 1.0}; // position std replaced by the attention radius, preprocessing.py:477-478
+    const double stdv[6] = {pos_std, pos_std, 2.0, 2.0, 1.0, 1.0}; // position std := the attention radius (preprocessing.py:477-478, 540)
     if (in_cluster && lane >= 1) {
         const int slot = __popc(ped_mask & ((1u << lane) - 1u));
         const size_t row_i = slot0 + slot;
@@ -229,13 +229,128 @@ __global__ void pred_ingest_kernel(const double *__restrict__ forecasts, const d
     }
 }
 
+// convert_to_mpc_state_vector (sicnav_acados.py:222-289) on the joint state SICNavAcados.predict builds (:1655-1681): one thread per env
+__global__ void pred_mpc_state_kernel(const double *__restrict__ robot, const double *__restrict__ humans, const double *__restrict__ goals,
+                                      const double *__restrict__ weights, int B, int H, int k, int joint, double *__restrict__ out,
+                                      double *__restrict__ theta)
+{
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= B) return;
+    const int nx_hum = joint ? 6 : 6 + k, nx = 10 + nx_hum * H + (joint ? k : 0);
+    const double *r = robot + (size_t)env * 9; // px py theta lvel omega v_dot omega_dot gx gy
+    double *v = out + (size_t)env * nx;
+    v[0] = r[0]; v[1] = r[1]; v[2] = sin(r[2]); v[3] = cos(r[2]);
+    v[4] = r[3]; v[5] = r[4]; v[6] = r[5]; v[7] = r[6]; v[8] = r[7]; v[9] = r[8];
+    for (int h = 0; h < H; ++h) {
+        const double *hs = humans + ((size_t)env * H + h) * 4; // px py vx vy
+        double *o = v + 10 + (size_t)h * nx_hum;
+        o[0] = hs[0]; o[1] = hs[1]; o[2] = hs[2]; o[3] = hs[3];
+        o[4] = goals[((size_t)env * H + h) * 2]; o[5] = goals[((size_t)env * H + h) * 2 + 1];
+        if (!joint)
+            for (int j = 0; j < k; ++j) o[6 + j] = weights[((size_t)env * H + h) * k + j];
+        if (theta) theta[(size_t)env * H + h] = (hs[2] != 0.0 || hs[3] != 0.0) ? atan2(hs[3], hs[2]) : 0.0; // :1678
+    }
+    if (joint)
+        for (int j = 0; j < k; ++j) v[nx - k + j] = weights[(size_t)env * k + j];
+}
+
+// the per-stage parameter vector handed to the solver (sicnav_acados.py:1389-1413): one thread per (env, stage, column)
+__global__ void pred_stage_params_kernel(const double *__restrict__ resh, const double *__restrict__ prefix, const double *__restrict__ stat,
+                                         int B, int horiz, int Tp, int HK, int n_prefix, int n_stat, double *__restrict__ out)
+{
+    const int np = n_prefix + 4 * HK + n_stat;
+    const size_t total = (size_t)B * (horiz + 1) * np;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % np), st = (int)((i / np) % (horiz + 1)), env = (int)(i / ((size_t)np * (horiz + 1)));
+        double val;
+        if (c < n_prefix) {
+            val = prefix[((size_t)env * (horiz + 1) + st) * n_prefix + c];
+        } else if (c < n_prefix + 4 * HK) {
+            const int q = (c - n_prefix) / HK, j = (c - n_prefix) % HK;          // q: X_t[:,0], X_t[:,1], X_t+1[:,0], X_t+1[:,1]
+            const int t = (st < horiz ? st : horiz - 1) + (q >> 1);               // the terminal stage reuses idx = horiz - 1 (:1403-1405)
+            val = resh[(((size_t)env * Tp + t) * HK + j) * 2 + (q & 1)];
+        } else {
+            val = stat[c - n_prefix - 4 * HK];
+        }
+        out[i] = val;
+    }
+}
+
+// CrowdSimPlus.step's `self.states.append([...])` (crowd_sim_plus.py:1175-1181) as a ring of L frames: slot <- positions before the step
+__global__ void state_log_push_kernel(const double *__restrict__ hpx, const double *__restrict__ hpy, const double *__restrict__ rpx,
+                                      const double *__restrict__ rpy, int B, int H, int L, int slot, double *__restrict__ log)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * (H + 1)) return;
+    const int env = i / (H + 1), a = i % (H + 1);
+    double *o = log + (((size_t)env * L + slot) * (H + 1) + a) * 2;
+    if (a < H) { o[0] = hpx[(size_t)env * H + a]; o[1] = hpy[(size_t)env * H + a]; }
+    else { o[0] = rpx[env]; o[1] = rpy[env]; }
+}
+
+// reset_scenario_values' history bootstrap (sicnav_acados.py:1163-1182): states[-Th-1:-1] -> the six ring frames, oldest first
+__global__ void pred_bootstrap_kernel(const double *__restrict__ log, int B, int H, int L, int newest, double *__restrict__ hist,
+                                      double *__restrict__ robot_hist)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * (H + 1) * TH) return;
+    const int f = i % TH, a = (i / TH) % (H + 1), env = i / (TH * (H + 1));
+    const int slot = ((newest - TH + f) % L + L) % L;        // frame f of states[-Th-1:-1]: the newest entry (states[-1]) is skipped
+    const double *src = log + (((size_t)env * L + slot) * (H + 1) + a) * 2;
+    double *dst = a < H ? hist + (((size_t)env * H + a) * TH + f) * 2 : robot_hist + ((size_t)env * TH + f) * 2;
+    dst[0] = src[0]; dst[1] = src[1];
+}
+
 } // namespace
 
-int snb_k_pred_prep(const double *hist, const double *robot_hist, int B, int H, double radius, double dt, int horizon,
+int snb_k_pred_mpc_state(const double *robot, const double *humans, const double *goals, const double *weights, int B, int H, int k,
+                         int joint, double *out, double *theta, cudaStream_t s)
+{
+    if (B == 0) return SNB_OK;
+    pred_mpc_state_kernel<<<(B + 127) / 128, 128, 0, s>>>(robot, humans, goals, weights, B, H, k, joint, out, theta);
+    snb_count_launch();
+    SNB_CUDA_TRY(cudaGetLastError());
+    return SNB_OK;
+}
+
+int snb_k_pred_stage_params(const double *resh, const double *prefix, const double *stat, int B, int horiz, int Tp, int HK, int n_prefix,
+                            int n_stat, double *out, cudaStream_t s)
+{
+    const size_t total = (size_t)B * (horiz + 1) * (n_prefix + 4 * HK + n_stat);
+    if (total == 0) return SNB_OK;
+    const size_t blocks = (total + 255) / 256;
+    pred_stage_params_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, s>>>(resh, prefix, stat, B, horiz, Tp, HK, n_prefix, n_stat, out);
+    snb_count_launch();
+    SNB_CUDA_TRY(cudaGetLastError());
+    return SNB_OK;
+}
+
+int snb_k_state_log_push(const double *hpx, const double *hpy, const double *rpx, const double *rpy, int B, int H, int L, int slot,
+                         double *log, cudaStream_t s)
+{
+    if (B == 0) return SNB_OK;
+    const int n = B * (H + 1);
+    state_log_push_kernel<<<(n + 127) / 128, 128, 0, s>>>(hpx, hpy, rpx, rpy, B, H, L, slot, log);
+    snb_count_launch();
+    SNB_CUDA_TRY(cudaGetLastError());
+    return SNB_OK;
+}
+
+int snb_k_pred_bootstrap(const double *log, int B, int H, int L, int newest, double *hist, double *robot_hist, cudaStream_t s)
+{
+    if (B == 0) return SNB_OK;
+    const int n = B * (H + 1) * TH;
+    pred_bootstrap_kernel<<<(n + 127) / 128, 128, 0, s>>>(log, B, H, L, newest, hist, robot_hist);
+    snb_count_launch();
+    SNB_CUDA_TRY(cudaGetLastError());
+    return SNB_OK;
+}
+
+int snb_k_pred_prep(const double *hist, const double *robot_hist, int B, int H, double radius, double pos_std, double dt, int horizon,
                     const PredPrepOut *out, cudaStream_t s)
 {
     if (B == 0) return SNB_OK;
-    pred_prep_kernel<<<(B + ENVS_PER_CTA - 1) / ENVS_PER_CTA, 32 * ENVS_PER_CTA, 0, s>>>(hist, robot_hist, B, H, radius, dt, horizon, *out);
+    pred_prep_kernel<<<(B + ENVS_PER_CTA - 1) / ENVS_PER_CTA, 32 * ENVS_PER_CTA, 0, s>>>(hist, robot_hist, B, H, radius, pos_std, dt, horizon, *out);
     snb_count_launch();
     SNB_CUDA_TRY(cudaGetLastError());
     return SNB_OK;

@@ -137,6 +137,11 @@ _proto("snb_pred_predict_host", C.c_int, [_vp, C.POINTER(_d), C.POINTER(_d), _i3
                                            C.POINTER(_d), C.POINTER(_d)], required=False)
 _proto("snb_pred_kde_topk", C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp], required=False)
 _proto("snb_pred_ingest", C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _d, _i32, _vp, _vp, _vp, _vp, _vp], required=False)
+_proto("snb_pred_set_position_std", C.c_int, [_vp, _d], required=False)
+_proto("snb_pred_mpc_pack", C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+       required=False)
+_proto("snb_env_log_push", C.c_int, [C.POINTER(CrowdState), _vp, _i32, _i32, _vp], required=False)
+_proto("snb_pred_bootstrap_history", C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp], required=False)
 
 
 def check(rc, what=""):

@@ -7,6 +7,7 @@ semantics incl. `starts_moving` warm-up, clamp, collision / frozen / goal / time
 the state of all environments as fp64 SoA arrays in HBM (snb.state.CrowdStateSoA) and advances them with
 snb_env_step.  There is no reference counterpart for the batching itself (SURVEY 8b "Python-side drop-ins").
 """
+import contextlib
 import ctypes as C
 
 import numpy as np
@@ -18,6 +19,8 @@ from .state import CrowdStateSoA, Obstacles
 
 
 class CrowdSimPlusBatch:
+    LOG_DEPTH = 7          # past_num_frames + 1 states: what the predictor's history bootstrap reads (sicnav_acados.py:1163-1182)
+
     def __init__(self, num_envs, device="cuda"):
         self.B = int(num_envs)
         self.device = torch.device(device)
@@ -34,7 +37,16 @@ class CrowdSimPlusBatch:
 
     # ------------------------------------------------------------------ configuration
     def configure(self, config):
-        """Same keys as CrowdSimPlus.configure (crowd_sim_plus.py:58-197), non-SB3 branch."""
+        """Same keys as CrowdSimPlus.configure (crowd_sim_plus.py:58-197), non-SB3 branch only: the SB3 branch whitelists rewards
+        per RL model and adds angular / linear smoothness terms (crowd_sim_plus.py:69-75, 94-100) that the kernel's reward table
+        does not have -- those configurations are refused instead of silently returning different rewards."""
+        if config.getboolean('env', 'SB3', fallback=False):
+            raise NotImplementedError("CrowdSimPlusBatch: [env] SB3 = True (per-model reward whitelist, RL observation spaces) is not implemented")
+        if config.getboolean('env', 'occlusion', fallback=False):
+            raise NotImplementedError("occlusion")           # as the reference (crowd_sim_plus.py:79-80)
+        for key in ('angular_smoothness_factor', 'linear_smoothness_factor'):
+            if config.has_option('reward', key) and float(config.get('reward', key)) != 0.0:
+                raise NotImplementedError(f"CrowdSimPlusBatch: [reward] {key} (action-smoothness penalty) is not implemented")
         self.config = config
         self.time_limit = config.getfloat('env', 'time_limit')
         self.time_step = config.getfloat('env', 'time_step')
@@ -125,8 +137,13 @@ class CrowdSimPlusBatch:
         self._door = door
         self.static_obstacles = [[(s[0], s[1]), (s[2], s[3])] for s in segs]
         self.obstacles = Obstacles(segs) if len(segs) else None
-        if self.sim_env == 'hallway_bottleneck' and getattr(self.human_policy, 'name', '') == 'sfm':
-            self.human_policy.is_bottleneck = True     # crowd_sim_plus.py:448-449
+        pol_name = self.config.get('humans', 'policy')
+        if self.sim_env in scenario.HALLWAY_RULES and pol_name not in ('orca_plus', 'sfm'):
+            raise RuntimeError("In hallway scenarios, human policy must be orca_plus or sfm, no other human policies supported due to "
+                               "static obstacles")           # generate_hallway_human, crowd_sim_plus.py:524-525
+        # the reference builds fresh Human / policy objects on every reset, so is_bottleneck starts False each time (:448-449)
+        if hasattr(self.human_policy, 'is_bottleneck') or pol_name == 'sfm':
+            self.human_policy.is_bottleneck = bool(self.sim_env == 'hallway_bottleneck' and pol_name == 'sfm')
         if on_device and not debug_case:
             cap = {'val': self.case_capacity['val'], 'test': self.case_capacity['test']}
             offset = {"train": cap["val"] + cap["test"], "val": 0, "test": cap["val"]}[phase]
@@ -160,11 +177,15 @@ class CrowdSimPlusBatch:
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._zero_action = torch.zeros(self.B, 2, dtype=torch.float64, device=self.device)
         self._cfgs = (self._policy_cfg(), self._door_cfg(), self._reward_cfg())
+        # `self.states` of the reference (crowd_sim_plus.py:1175-1181) as a ring of the last LOG_DEPTH pre-step positions
+        self.state_log = torch.zeros(self.B, self.LOG_DEPTH, H + 1, 2, dtype=torch.float64, device=self.device) if self.LOG_DEPTH else None
+        self.n_logged = 0
         if self.starts_moving > 0:
             st.global_time.fill_(-self.starts_moving * self.time_step)
             for _ in range(self.starts_moving):
                 self._launch(self._zero_action, None)
         st.prev_dist.copy_(torch.hypot(st.rpx - st.rgx, st.rpy - st.rgy))
+        self.check_status()         # a device capacity overflow during the warm-up steps must not go unnoticed
         return self.observation()
 
     # ------------------------------------------------------------------ step
@@ -177,6 +198,10 @@ class CrowdSimPlusBatch:
             self._argc_tail = (_capi.ptr(self.reward), _capi.ptr(self.dmin), _capi.ptr(self.flags))
             self._argc_status = _capi.ptr(self.status)
         pc, dc, rc, st = self._argc
+        if self.state_log is not None:
+            _capi.check(_capi.lib.snb_env_log_push(C.byref(st), _capi.ptr(self.state_log), self.LOG_DEPTH, self.n_logged % self.LOG_DEPTH,
+                                                   _capi.stream_ptr(stream)), "snb_env_log_push")
+            self.n_logged += 1
         _capi.check(_capi.lib.snb_env_step(pc, dc, rc, C.byref(st),
                                            self.obstacles.handle if self.obstacles is not None else None,
                                            _capi.ptr(action), _capi.ptr(active), *self._argc_tail,
@@ -185,14 +210,18 @@ class CrowdSimPlusBatch:
 
     def step(self, robot_action, stream=None, nbr=None, nbr_cnt=None):
         """robot_action: [B,2] fp64 CUDA tensor, (vx,vy) or (v,r).  Returns (reward[B], done[B] bool, flags[B]) on the
-        device; state advances in place.  Environments that finished are frozen when `freeze_done`."""
+        device; state advances in place.  With `freeze_done`, environments that finished are frozen: the kernel skips them and
+        their reward / flags read 0 from then on (so summing rewards over an episode does not re-count the terminal reward).
+        A device-side capacity overflow (more than 32 ORCA lines / obstacle neighbours) is raised by check_status(), which
+        reset() and rollouts call; a single step does not synchronise."""
         a = robot_action
         if not (isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.float64 and a.is_contiguous()):
             a = torch.as_tensor(np.asarray(a, np.float64).reshape(self.B, 2)).to(self.device)
-        self._launch(a, self.active if self.freeze_done else None, stream, nbr, nbr_cnt)
-        done = self.flags >= _capi.F_DONE            # F_DONE is the highest flag bit: one compare instead of and + ne
-        if self.freeze_done:
-            self.active &= (~done).to(torch.uint8)
+        with torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext():
+            self._launch(a, self.active if self.freeze_done else None, stream, nbr, nbr_cnt)
+            done = self.flags >= _capi.F_DONE            # F_DONE is the highest flag bit: one compare instead of and + ne
+            if self.freeze_done:
+                self.active &= (~done).to(torch.uint8)
         return self.reward, done, self.flags
 
     def what_if(self, robot_actions, stream=None):

@@ -8,7 +8,6 @@ Two faces over the same C ABI:
 torch tensors only hold weights and I/O buffers; every computation is in libsnb.so (no CPU path).
 """
 import ctypes as C
-import pickle
 
 import numpy as np
 import torch
@@ -16,12 +15,9 @@ import torch
 from .. import _capi
 from .denoiser import JmidDenoiser
 
-ENC_MODULES = {
-    "node_history": "PEDESTRIAN/node_history_encoder",
-    "edge_ped": "PEDESTRIAN->PEDESTRIAN/edge_encoder",
-    "edge_robot": "PEDESTRIAN->JRDB_ROBOT/edge_encoder",
-}
-ATT = "PEDESTRIAN/edge_influence_encoder"
+from .weights import ATT, ENC_MODULES as _ENC, load_checkpoint, resolve_model_path  # noqa: F401  (load_checkpoint re-exported)
+
+ENC_MODULES = {k: v[0] for k, v in _ENC.items()}
 
 
 def encoder_struct(enc, device):
@@ -42,43 +38,59 @@ def encoder_struct(enc, device):
     return w, keep
 
 
-class _TolerantUnpickler(pickle.Unpickler):
-    """The reference pickles whole nn.Modules (`registrar.model_dict`, mid.py:1502-1505); their classes live in the reference
-    tree.  Classes that cannot be imported are replaced by bare nn.Module subclasses: only the parameters are needed."""
-
-    def find_class(self, module, name):
+def read_mid_config(mid_config_file):
+    """`MID.__init__` accepts a yaml PATH or an EasyDict (mid.py:83-89); the simulator passes the path
+    "sicnav_diffusion/JMID/test_time_configs/mid_jp.yaml" (sicnav_acados.py:998).  Returns a plain dict."""
+    if mid_config_file is None:
+        return {}
+    if isinstance(mid_config_file, (str, bytes)) or hasattr(mid_config_file, "__fspath__"):
+        import os
+        path = os.fspath(mid_config_file)
+        if not os.path.isfile(path):
+            alt = os.path.join(os.environ.get("SNB_REFERENCE", "/root/reference"), path)
+            if os.path.isfile(alt):
+                path = alt
+        with open(path) as f:
+            text = f.read()
         try:
-            return super().find_class(module, name)
-        except (ImportError, AttributeError):
-            return type(name, (torch.nn.Module,), {"__module__": module})
+            import yaml
+            return dict(yaml.safe_load(text))
+        except ImportError:
+            return _parse_flat_yaml(text)
+    if isinstance(mid_config_file, dict):
+        return dict(mid_config_file)
+    return dict(vars(mid_config_file))
 
 
-class _TolerantPickle:
-    __name__ = "pickle"
-    Unpickler = _TolerantUnpickler
-    load = staticmethod(lambda f, **kw: _TolerantUnpickler(f, **kw).load())
-    loads = staticmethod(pickle.loads)
-    dump = staticmethod(pickle.dump)
-    dumps = staticmethod(pickle.dumps)
-    PickleError = pickle.PickleError
-    UnpicklingError = pickle.UnpicklingError
+def _parse_flat_yaml(text):
+    """The test-time configs are flat `key: scalar | [list]` files; enough of YAML for them when PyYAML is absent."""
+    out = {}
+    for line in text.splitlines():
+        line = line.split("#", 1)[0].strip()
+        if not line or ":" not in line:
+            continue
+        k, v = (x.strip() for x in line.split(":", 1))
+        if v.startswith("[") and v.endswith("]"):
+            out[k] = [_yaml_scalar(x.strip()) for x in v[1:-1].split(",") if x.strip()]
+        else:
+            out[k] = _yaml_scalar(v)
+    return out
 
 
-def load_checkpoint(path):
-    """Reads a reference checkpoint {"encoder": ModuleDict, "ddpm": state_dict} (mid.py:1231-1232, 1291) ->
-    (encoder dict "<module>/<param>" -> tensor, ddpm state_dict)."""
-    try:
-        ck = torch.load(path, map_location="cpu", weights_only=False)
-    except (ImportError, AttributeError, ModuleNotFoundError):
-        ck = torch.load(path, map_location="cpu", weights_only=False, pickle_module=_TolerantPickle)
-    enc = {}
-    md = ck["encoder"]
-    items = md.items() if hasattr(md, "items") else md._modules.items()
-    for mod_name, mod in items:
-        params = mod.named_parameters() if hasattr(mod, "named_parameters") else mod.items()
-        for pname, t in params:
-            enc[f"{mod_name}/{pname}"] = t.detach() if hasattr(t, "detach") else torch.as_tensor(t)
-    return enc, ck["ddpm"]
+def _yaml_scalar(v):
+    low = v.lower()
+    if low in ("true", "yes", "on"):
+        return True
+    if low in ("false", "no", "off"):
+        return False
+    if low in ("none", "null", "~", ""):
+        return None if low != "none" else "None"     # PyYAML reads a bare `None` as the string 'None'
+    for cast in (int, float):
+        try:
+            return cast(v)
+        except ValueError:
+            pass
+    return v.strip("'\"")
 
 
 class ForecasterBatch:
@@ -181,6 +193,43 @@ class ForecasterBatch:
                                               _capi.stream_ptr(stream)), "snb_pred_ingest")
         return resh, wts, goals, vpref
 
+    def set_position_std(self, pos_std):
+        """0 (default): positions are standardised by the attention radius like the reference (preprocessing.py:477-478);
+        a positive value pins the scale (benchmarks that widen `radius` only to force A = H)."""
+        _capi.check(_capi.lib.snb_pred_set_position_std(self._h, float(pos_std)), "snb_pred_set_position_std")
+
+    def bootstrap_history(self, state_log, newest, stream=None):
+        """reset_scenario_values (sicnav_acados.py:1163-1182): rings <- env.states[-7:-1]; state_log [B,L,H+1,2] fp64 CUDA ring
+        (CrowdSimPlusBatch.state_log), `newest` = slot of the last logged state."""
+        B, L = state_log.shape[0], state_log.shape[1]
+        assert state_log.is_cuda and state_log.dtype == torch.float64 and state_log.is_contiguous() and tuple(state_log.shape) == (B, L, self.H + 1, 2)
+        _capi.check(_capi.lib.snb_pred_bootstrap_history(self._h, _capi.ptr(state_log), L, int(newest), B, _capi.stream_ptr(stream)),
+                    "snb_pred_bootstrap_history")
+
+    def mpc_pack(self, robot, humans, goals, weights, resh=None, horiz=4, stage_prefix=None, static_obs=None, stream=None):
+        """convert_to_mpc_state_vector (sicnav_acados.py:222-289) + the per-stage parameter vectors (:1389-1413).
+        robot [B,9] = px,py,theta,lvel,omega,v_dot,omega_dot,gx,gy; humans [B,H,4] = px,py,vx,vy; goals / weights / resh from ingest().
+        -> mpc_state [B, 10+nX_hums], human_theta [B,H], stage_params [B, horiz+1, n_prefix + 4*H*k + n_static] (None without resh)."""
+        B = robot.shape[0]
+        for t, shp in ((robot, (B, 9)), (humans, (B, self.H, 4)), (goals, (B, self.H, 2))):
+            assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == shp, (t.shape, shp)
+        nx = 10 + (6 * self.H + self.k if self.joint else (6 + self.k) * self.H)
+        state = torch.empty(B, nx, dtype=torch.float64, device=self.device)
+        theta = torch.empty(B, self.H, dtype=torch.float64, device=self.device)
+        n_prefix = 0 if stage_prefix is None else int(stage_prefix.shape[-1])
+        n_static = 0 if static_obs is None else int(static_obs.numel())
+        params = None
+        if resh is not None:
+            assert tuple(resh.shape) == (B, horiz + 1, self.H * self.k, 2), resh.shape
+            if stage_prefix is not None:
+                assert tuple(stage_prefix.shape) == (B, horiz + 1, n_prefix) and stage_prefix.is_contiguous()
+            params = torch.empty(B, horiz + 1, n_prefix + 4 * self.H * self.k + n_static, dtype=torch.float64, device=self.device)
+        _capi.check(_capi.lib.snb_pred_mpc_pack(_capi.ptr(robot), _capi.ptr(humans), _capi.ptr(goals), _capi.ptr(weights), _capi.ptr(resh),
+                                                _capi.ptr(stage_prefix), _capi.ptr(static_obs), B, self.H, self.k, self.T, int(horiz),
+                                                int(self.joint), n_prefix, n_static, _capi.ptr(state), _capi.ptr(theta), _capi.ptr(params),
+                                                _capi.stream_ptr(stream)), "snb_pred_mpc_pack")
+        return state, theta, params
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
@@ -206,15 +255,31 @@ def randn(shape, seed, offset=0, device="cuda"):
     return out
 
 
+class _MidModelFacade:
+    """What callers reach through `forecaster.mid_model` / `.model` in the reference (mid.py:73-104): `num_samples`, `config`."""
+
+    def __init__(self, cfg, drawn):
+        self.config = type("MidConfig", (dict,), {"__getattr__": lambda s_, k: s_[k]})(cfg)
+        self.num_samples = drawn
+        self.sicnav_inference = True
+
+
 class HumanTrajectoryForecasterSim:
-    """Drop-in for mid_sim_wrapper.HumanTrajectoryForecasterSim (B = 1).
+    """Drop-in for mid_sim_wrapper.HumanTrajectoryForecasterSim (B = 1), constructed exactly as the reference does
+    (sicnav_acados.py:996-1000):  HumanTrajectoryForecasterSim(env_config=<RawConfigParser>, mid_config_file="<...>/mid_jp.yaml").
 
-    env_config: configparser with [human_trajectory_forecaster] past_num_frames / prediction_horizon / num_samples,
-    [env] time_step, [sim] human_num (mid_sim_wrapper.py:171-195).  mid_config: mapping / attribute object with model_path,
-    num_samples (drawn), step_size, joint_prediction (test_time_configs/mid_jp.yaml), or `weights=(encoder, ddpm)`."""
+    env_config: [human_trajectory_forecaster] publish_freq / past_num_frames / prediction_horizon / num_samples, [env] time_step,
+    [sim] human_num (mid_sim_wrapper.py:171-195).  mid_config_file: yaml path, mapping or attribute object with `model_path`,
+    `diffnet` (JointPredictionTransformerConcatLinear = JMID, TransformerConcatLinear = iMID), `num_samples` (drawn), `step_size`,
+    `sampling` (test_time_configs/mid_jp.yaml).  `weights=(encoder, ddpm)` bypasses the checkpoint file (tests).
+    Restrictions, stated: past_num_frames must be 6 (the shipped value) and the history frames must be time_step apart, so the
+    reference's resampling / interpolation (mid_sim_wrapper.py:283-310) is the identity; sampling must be "ddim"."""
 
-    def __init__(self, env_config, mid_config_file=None, weights=None, device="cuda", seed=0):
+    def __init__(self, env_config=None, mid_config_file=None, weights=None, device="cuda", seed=0):
+        if env_config is None:
+            raise _capi.SnbError("HumanTrajectoryForecasterSim: env_config is required (the reference's default path is a ROS file)")
         g = env_config
+        self.publish_freq = g.getfloat("human_trajectory_forecaster", "publish_freq", fallback=0.0)
         self.time_step = g.getfloat("env", "time_step")
         self.num_hist_frames = g.getint("human_trajectory_forecaster", "past_num_frames")
         self.predict_horizon = g.getint("human_trajectory_forecaster", "prediction_horizon")
@@ -222,13 +287,23 @@ class HumanTrajectoryForecasterSim:
         self.num_hums = g.getint("sim", "human_num")
         if self.num_hist_frames != 6:
             raise _capi.SnbError("snb predictor: past_num_frames must be 6 (the shipped configuration)")
-        cfg = {} if mid_config_file is None else (dict(mid_config_file) if isinstance(mid_config_file, dict) else dict(vars(mid_config_file)))
-        enc, ddpm = weights if weights is not None else load_checkpoint(cfg["model_path"])
+        cfg = read_mid_config(mid_config_file)
+        if str(cfg.get("sampling", "ddim")) != "ddim":
+            raise _capi.SnbError("snb predictor: only sampling = ddim (the shipped test-time setting) is implemented")
+        diffnet = cfg.get("diffnet")
+        if diffnet is None:
+            joint = bool(cfg.get("joint_prediction", True))
+        elif diffnet in ("JointPredictionTransformerConcatLinear", "TransformerConcatLinear"):
+            joint = diffnet == "JointPredictionTransformerConcatLinear"
+        else:
+            raise _capi.SnbError(f"snb predictor: unknown diffnet {diffnet!r}")
+        enc, ddpm = weights if weights is not None else load_checkpoint(resolve_model_path(cfg["model_path"]))
         drawn = int(cfg.get("num_samples", 20))
         self.batch = ForecasterBatch(enc, ddpm, max_envs=1, H=self.num_hums, num_samples=drawn,
                                      num_ret=min(self.num_ret_samples, drawn), step_size=int(cfg.get("step_size", 20)),
-                                     horizon=self.predict_horizon, joint=bool(cfg.get("joint_prediction", True)), dt=self.time_step,
-                                     device=device, seed=seed)
+                                     horizon=self.predict_horizon, joint=joint, dt=self.time_step, device=device, seed=seed)
+        self.mid_model = self.model = _MidModelFacade(cfg, drawn)
+        self.mid_env = None          # the Trajectron Environment object has no counterpart: scenes are built on the device
         self.prev_states = [[] for _ in range(self.num_hums)]
         self.prev_robot_states = []
 
@@ -241,10 +316,43 @@ class HumanTrajectoryForecasterSim:
         if len(self.prev_robot_states) > self.num_hist_frames:   # the reference keeps it unbounded but only uses the joined tail
             self.prev_robot_states.pop(0)
 
+    def _histories(self):
+        hist = np.asarray(self.prev_states, np.float64)
+        rob = np.asarray(self.prev_robot_states[-self.num_hist_frames:], np.float64)
+        ts = hist[0, :, 2]
+        if not (np.allclose(np.diff(ts), self.time_step, atol=1e-9) and np.allclose(rob[:, 2], ts, atol=1e-9)):
+            raise _capi.SnbError("snb predictor: history frames must be exactly time_step apart (resampling is not implemented)")
+        return hist[None, :, :, :2], rob[None, :, :2]
+
     def predict_ret_best(self, noise=None):
+        """-> (forecasts [H, k, T+1, 2] float64, log-weights [H, k] float64), mid_sim_wrapper.py:482-509."""
         if len(self.prev_states[0]) < self.num_hist_frames:
             raise _capi.SnbError("predict_ret_best: fewer than past_num_frames history frames")
-        hist = np.asarray(self.prev_states, np.float64)[None, :, :, :2]
-        rob = np.asarray(self.prev_robot_states[-self.num_hist_frames:], np.float64)[None, :, :2]
+        hist, rob = self._histories()
         fc, lw = self.batch.predict_host(hist, rob, None if noise is None else noise[None])
         return fc[0], lw[0]
+
+    def predict(self, noise=None):
+        """mid_sim_wrapper.py:456-479: None until past_num_frames frames are held, then ALL drawn samples with the current pose
+        prepended, [H, S, T+1, 2].  (The reference body calls convert_to_mid_state_env with one argument and unpacks two of its five
+        results, so it raises as shipped; this is its evident intent.)"""
+        if len(self.prev_states[0]) < self.num_hist_frames:
+            return None
+        k0 = self.batch.k
+        self.batch.k = self.batch.S
+        try:
+            hist, rob = self._histories()
+            fc, _ = self.batch.predict_host(hist, rob, None if noise is None else noise[None])
+        finally:
+            self.batch.k = k0
+        return fc[0]
+
+    def get_most_likely_samples(self, forecasts):
+        """forecasts [S, A, T, 2] (torch or numpy) -> (top-k forecasts [A, k, T, 2], log-weights [A, k]) like
+        mid_sim_wrapper.get_most_likely_samples(forecasts, model, num_ret_samples) (:14-169, :440-441)."""
+        f = torch.as_tensor(forecasts, dtype=torch.float32, device=self.batch.device).contiguous()
+        S, A = int(f.shape[0]), int(f.shape[1])
+        k = min(self.num_ret_samples, S)
+        sel, lw = kde_topk(f[None], k)
+        top = f[sel[0].long()].permute(1, 0, 2, 3).contiguous()
+        return top, lw[0].to(torch.float32)[None].expand(A, k)
