@@ -25,6 +25,8 @@ static double npnorm2(double x, double y) { return sqrt(fma(y, y, x * x)); }
 
 /* ------------------------------------------------------------------------- */
 /* crowd_sim_plus/envs/policy/orca.py:82-133 and orca_plus.py:29-90          */
+static __thread OrcProbe *g_probe = NULL;
+
 void orc_orca_predict(const OrcPolicyCfg *cfg, const double *self8, int n_others, const double *others,
                       int n_seg, const double *segs, double *out_v2, int *nbr_ids, int *n_nbr,
                       int *obst_nbr_ids, int *n_obst_nbr)
@@ -67,6 +69,16 @@ void orc_orca_predict(const OrcPolicyCfg *cfg, const double *self8, int n_others
     float v[2];
     rvo_get_agent_velocity(sim, 0, v);
     out_v2[0] = (double)v[0]; out_v2[1] = (double)v[1];
+    if (g_probe) { /* introspection for tests/test_orca_properties.py: agent 0's half-planes as RVO2 built them */
+        OrcProbe *pr = g_probe;
+        pr->n_lines = rvo_get_agent_num_orca_lines(sim, 0);
+        pr->n_obst_lines = pr->n_lines - rvo_get_agent_num_agent_neighbors(sim, 0);
+        for (int k = 0; k < pr->n_lines && k < ORC_PROBE_MAX_LINES; ++k) rvo_get_agent_orca_line(sim, 0, k, pr->lines + 4 * k);
+        float pv[2];
+        rvo_get_agent_pref_velocity(sim, 0, pv);
+        pr->pref[0] = pv[0]; pr->pref[1] = pv[1];
+        pr->max_speed = rvo_get_agent_max_speed(sim, 0);
+    }
     if (n_nbr) {
         *n_nbr = rvo_get_agent_num_agent_neighbors(sim, 0);
         for (int k = 0; k < *n_nbr; ++k) nbr_ids[k] = rvo_get_agent_agent_neighbor(sim, 0, k) - 1; /* ob index */
@@ -538,4 +550,21 @@ void orc_env_step(const OrcPolicyCfg *pcfg, const OrcDoorCfg *door, const OrcRew
 {
     StepArgs a = { pcfg, door, rcfg, st, robot_action, active, reward, dmin, flags, nbr, nbr_cnt };
     parallel_for(step_range, &a, st->B, n_threads);
+}
+
+
+/* n_cases independent ORCA.predict / ORCAPlus.predict calls (case c: self8[c], the first n_others[c] rows of others[c, E, 5]) with the
+ * half-planes, preferred velocity and max speed agent 0 ended up with, for the property tests. */
+void orc_orca_probe(const OrcPolicyCfg *cfg, int n_cases, const double *self8, int E, const double *others, const int *n_others,
+                    int n_seg, const double *segs, double *out_v, OrcProbe *probes)
+{
+    for (int c = 0; c < n_cases; ++c) {
+        g_probe = probes + c;
+        int ids[64], cnt = 0;
+        orc_orca_predict(cfg, self8 + 8 * (size_t)c, n_others[c], others + 5 * (size_t)E * c, n_seg, segs, out_v + 2 * (size_t)c,
+                         cfg->max_neighbors <= 64 ? ids : NULL, cfg->max_neighbors <= 64 ? &cnt : NULL, NULL, NULL);
+        probes[c].n_agent_nbr = cnt;
+        for (int k = 0; k < cnt && k < 16; ++k) probes[c].nbr_ids[k] = ids[k];
+    }
+    g_probe = NULL;
 }

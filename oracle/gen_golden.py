@@ -521,6 +521,48 @@ def gen_ckpt():
     np.savez_compressed(os.path.join(OUT, "ckpt_c4_cases.npz"), **out)
 
 
+def gen_ingest():
+    """tests/golden/ingest_cases.npz: SICNavAcados.convert_to_mpc_state_vector (sicnav_acados.py:222-289) EXECUTED from the reference
+    source.  The module cannot be imported (casadi / acados), so the method's own source text is cut out of the file with `ast` at
+    generation time and exec'd against a stub `self` carrying the attributes it reads (mpc_env.nx_r / np_g / nX_hums / nx_hum /
+    num_hums / num_MID_samples, human_pred_MID, human_pred_MID_joint, prev_rev)."""
+    import ast
+    import types
+    src_path = os.path.join(ref_shims.REF, "sicnav_diffusion/policy/sicnav_acados.py")
+    src = open(src_path).read()
+    fn = None
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.FunctionDef) and node.name == "convert_to_mpc_state_vector":
+            fn = node
+    assert fn is not None
+    ns = {"np": np}
+    import textwrap
+    exec(textwrap.dedent(ast.get_source_segment(src, fn)), ns)
+    convert = ns["convert_to_mpc_state_vector"]
+    rng = np.random.default_rng(99)
+    out = {}
+    for tag, joint, H, k in (("jmid_h10_k20", True, 10, 20), ("jmid_h3_k15", True, 3, 15), ("imid_h5_k8", False, 5, 8)):
+        nx_hum = 6 if joint else 6 + k
+        mpc_env = types.SimpleNamespace(nx_r=8, np_g=2, nx_hum=nx_hum, num_hums=H, num_MID_samples=k,
+                                        nX_hums=nx_hum * H + (k if joint else 0))
+        self_ = types.SimpleNamespace(mpc_env=mpc_env, human_pred_MID=True, human_pred_MID_joint=joint, prev_rev=False)
+        robot = rng.uniform(-2, 2, 9)
+        humans = rng.uniform(-3, 3, (H, 4)); humans[1, 2:] = 0.0            # a human at rest: theta = 0 branch (:1678)
+        goals = rng.uniform(-4, 4, (H, 2))
+        w = np.log(rng.dirichlet(np.ones(k), size=None if joint else H))
+        rs = types.SimpleNamespace(px=robot[0], py=robot[1], theta=robot[2], lvel=robot[3], omega=robot[4], v_dot=robot[5],
+                                   omega_dot=robot[6], gx=robot[7], gy=robot[8], velocity=(0.0, 0.0))
+        hs = [types.SimpleNamespace(px=h[0], py=h[1], vx=h[2], vy=h[3], gx=g[0], gy=g[1]) for h, g in zip(humans, goals)]
+        state = types.SimpleNamespace(self_state=rs, human_states=hs)
+        val = convert(self_, state, 8, 2, mpc_env.nX_hums, w, get_numpy=True)
+        out[f"{tag}_robot"] = robot; out[f"{tag}_humans"] = humans; out[f"{tag}_goals"] = goals; out[f"{tag}_weights"] = w
+        out[f"{tag}_val"] = np.asarray(val).reshape(-1); out[f"{tag}_joint"] = np.array(int(joint))
+    np.savez_compressed(os.path.join(OUT, "ingest_cases.npz"), **out)
+    print("ingest:", sorted(out))
+
+
+if "ingest" in sys.argv[1:]:
+    gen_ingest()
 if "predictor" in sys.argv[1:]:
     with np.errstate(all="ignore"):
         gen_predictor()

@@ -56,6 +56,14 @@ class EnvState(C.Structure):
          ("global_time", _DP), ("prev_dist", _DP), ("n_seg", C.c_int), ("segs", _DP)]
 
 
+PROBE_MAX_LINES = 48
+
+
+class OrcProbe(C.Structure):
+    _fields_ = [("n_lines", C.c_int), ("n_obst_lines", C.c_int), ("n_agent_nbr", C.c_int), ("nbr_ids", C.c_int * 16),
+                ("lines", C.c_float * (4 * PROBE_MAX_LINES)), ("pref", C.c_float * 2), ("max_speed", C.c_float)]
+
+
 POLICY_ORCA, POLICY_ORCA_PLUS, POLICY_SFM = 0, 1, 2
 KIN_HOLONOMIC, KIN_UNICYCLE = 0, 1
 F_REACHED, F_TIMEOUT, F_COLLISION, F_WALL, F_FROZEN, F_DANGER, F_DONE = 1, 2, 4, 8, 16, 32, 64
@@ -106,6 +114,8 @@ def lib():
         L.orc_env_step.argtypes = [C.POINTER(PolicyCfg), C.POINTER(DoorCfg), C.POINTER(RewardCfg), C.POINTER(EnvState),
                                    _DP, C.POINTER(C.c_ubyte), _DP, _DP, ip, ip, ip, C.c_int]
         L.orc_policy_batch.argtypes = [C.POINTER(PolicyCfg), C.POINTER(EnvState), _DP, ip, ip, C.c_int]
+        L.orc_orca_probe.argtypes = [C.POINTER(PolicyCfg), C.c_int, _DP, C.c_int, _DP, ip, C.c_int, _DP, _DP, C.POINTER(OrcProbe)]
+        L.rvo_branch_counters.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
         _lib = L
     return _lib
 
@@ -208,3 +218,30 @@ def env_step(pcfg, door, rcfg, env, robot_action, active=None, n_threads=1, want
     if want_nbr:
         return reward, dmin, flags, nbr.reshape(B, H, MN), cnt.reshape(B, H)
     return reward, dmin, flags
+
+
+def orca_probe(pcfg, self8, others, n_others, segs=None):
+    """n independent ORCA(.Plus).predict calls: self8 [n,8], others [n,E,5], n_others [n] -> dict(v [n,2] float64 (float32 values),
+    lines [n,PROBE_MAX_LINES,4] float32 (point, direction; obstacle lines first), n_lines, n_obst_lines, nbr [n,16], n_nbr,
+    pref [n,2], max_speed [n])."""
+    L = lib()
+    self8 = np.ascontiguousarray(self8, np.float64); others = np.ascontiguousarray(others, np.float64)
+    n, E = others.shape[0], others.shape[1]
+    n_others = np.ascontiguousarray(n_others, np.int32)
+    segs = np.zeros((0, 4)) if segs is None else np.ascontiguousarray(np.asarray(segs, np.float64).reshape(-1, 4))
+    out_v = np.zeros((n, 2), np.float64)
+    probes = (OrcProbe * n)()
+    L.orc_orca_probe(C.byref(pcfg), n, dptr(self8.reshape(-1)), E, dptr(others.reshape(-1)), iptr(n_others), len(segs),
+                     dptr(segs.reshape(-1)) if len(segs) else None, dptr(out_v.reshape(-1)), probes)
+    raw = np.frombuffer(probes, dtype=np.dtype([("n_lines", "i4"), ("n_obst_lines", "i4"), ("n_agent_nbr", "i4"), ("nbr_ids", "i4", 16),
+                                                ("lines", "f4", (PROBE_MAX_LINES, 4)), ("pref", "f4", 2), ("max_speed", "f4")]))
+    assert raw.shape[0] == n
+    return dict(v=out_v, lines=raw["lines"].copy(), n_lines=raw["n_lines"].copy(), n_obst_lines=raw["n_obst_lines"].copy(),
+                nbr=raw["nbr_ids"].copy(), n_nbr=raw["n_agent_nbr"].copy(), pref=raw["pref"].astype(np.float64),
+                max_speed=raw["max_speed"].astype(np.float64))
+
+
+def branch_counters(reset=False):
+    out = (C.c_ulonglong * 48)()
+    lib().rvo_branch_counters(out, int(reset))
+    return np.array(out[:], dtype=np.int64)

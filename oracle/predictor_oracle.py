@@ -230,3 +230,53 @@ def mpc_ingest(forecasts, logw, dt=0.25, horiz=4, joint=True):
     goals = np.array([[np.mean(fc[h, :, 0, 0]), np.mean(fc[h, :, 0, 1])] for h in range(H)])    # per human, as the reference loops
     v = np.linalg.norm(np.diff(fc, axis=2), axis=-1) / dt                           # on the forecasts WITHOUT the current pose (:1667)
     return resh, weights, goals, v.max(axis=(1, 2))
+
+
+def mpc_state_vector(robot, humans, goals, weights, joint=True):
+    """SICNavAcados.convert_to_mpc_state_vector (sicnav_diffusion/policy/sicnav_acados.py:222-289) on the joint state that
+    SICNavAcados.predict builds (:1655-1681).  robot = (px, py, theta, lvel, omega, v_dot, omega_dot, gx, gy); humans [H,4] =
+    px, py, vx, vy; goals [H,2]; weights [k] (JMID) or [H,k] (iMID).  nx_r = 8, np_g = 2, nx_hum = 6 (+ k for iMID)
+    (utils/mpc_utils/mpc_env_new.py:72-104).  Returns (val [nx], human_theta [H])."""
+    H = humans.shape[0]
+    k = weights.shape[-1]
+    nx_hum = 6 if joint else 6 + k
+    val = np.zeros(8 + 2 + nx_hum * H + (k if joint else 0))
+    val[0], val[1] = robot[0], robot[1]
+    val[2], val[3] = np.sin(robot[2]), np.cos(robot[2])
+    val[4:8] = robot[3:7]
+    val[8], val[9] = robot[7], robot[8]
+    off = 10
+    for i in range(H):
+        val[off + i * nx_hum: off + i * nx_hum + 4] = humans[i]
+        val[off + i * nx_hum + 4: off + i * nx_hum + 6] = goals[i]
+        if not joint:
+            val[off + i * nx_hum + 6: off + (i + 1) * nx_hum] = weights[i, :]
+    if joint:
+        val[-k:] = weights[:]
+    theta = np.array([np.arctan2(h[3], h[2]) if (h[2] != 0 or h[3] != 0) else 0.0 for h in humans])      # :1678
+    return val, theta
+
+
+def stage_params(resh, horiz, prefix=None, static_obs=None):
+    """The parameter vector set on every solver stage (sicnav_acados.py:1389-1413): np.hstack([x_ref_k, u_ref_k, Q, R, Q_T (the
+    `prefix`, MPC-side), X_t[:,0], X_t[:,1], X_t+1[:,0], X_t+1[:,1] (, static obstacles)]); stage `horiz` reuses t = horiz - 1.
+    resh = forecasts_reshaped [horiz+1, H*k, 2].  Returns [horiz+1, n_prefix + 4*H*k + n_static]."""
+    rows = []
+    for idx in range(horiz + 1):
+        t = idx if idx < horiz else horiz - 1
+        parts = [] if prefix is None else [prefix[idx]]
+        parts += [resh[t][:, 0], resh[t][:, 1], resh[t + 1][:, 0], resh[t + 1][:, 1]]
+        if static_obs is not None:
+            parts.append(np.asarray(static_obs).reshape(-1))
+        rows.append(np.hstack(parts))
+    return np.stack(rows)
+
+
+def bootstrap_history(states, num_hist_frames=6):
+    """reset_scenario_values (sicnav_acados.py:1163-1182): a fresh forecaster is fed env.states[-Th-1:-1] -- the newest logged state
+    is NOT used -- stamped (global_time_step - Th ... global_time_step - 1) * dt.  states: list of [H+1,2] position arrays (robot
+    last), oldest first.  Returns (hist [H,Th,2], robot_hist [Th,2])."""
+    if len(states) < num_hist_frames + 1:
+        raise IndexError("not enough logged states (starts_moving too small)")
+    sel = np.stack(states[-num_hist_frames - 1:-1])             # [Th, H+1, 2]
+    return np.ascontiguousarray(sel[:, :-1].transpose(1, 0, 2)), np.ascontiguousarray(sel[:, -1])

@@ -16,6 +16,20 @@ typedef struct { float x, y; } V2;
 typedef struct { V2 point, direction; } Line;
 
 /* ---- Vector2.h (Appendix A preamble) ---- */
+/* Branch coverage counters for tests/test_orca_properties.py (which geometric case of Agent::computeNewVelocity / linearProgram1-3
+ * a test population actually exercised).  Pure instrumentation: no arithmetic depends on them. */
+enum { RVO_NBRANCH = 48 };
+static unsigned long long g_branch[RVO_NBRANCH];
+static __thread int g_br_on = 0; /* counted only while agent 0 (the agent the policy reads back) is processed */
+#define BR(k) do { if (g_br_on) __atomic_fetch_add(&g_branch[(k)], 1ULL, __ATOMIC_RELAXED); } while (0)
+void rvo_branch_counters(unsigned long long *out, int reset)
+{
+    for (int i = 0; i < RVO_NBRANCH; ++i) {
+        out[i] = __atomic_load_n(&g_branch[i], __ATOMIC_RELAXED);
+        if (reset) __atomic_store_n(&g_branch[i], 0ULL, __ATOMIC_RELAXED);
+    }
+}
+
 static inline V2 v2(float x, float y) { V2 r; r.x = x; r.y = y; return r; }
 static inline V2 vadd(V2 a, V2 b) { return v2(a.x + b.x, a.y + b.y); }
 static inline V2 vsub(V2 a, V2 b) { return v2(a.x - b.x, a.y - b.y); }
@@ -360,7 +374,7 @@ static int linearProgram1(const Line *lines, int lineNo, float radius, V2 optVel
 {
     const float dotProduct = vdot(lines[lineNo].point, lines[lineNo].direction);
     const float discriminant = sqr(dotProduct) + sqr(radius) - absSq(lines[lineNo].point);
-    if (discriminant < 0.0f) return 0;
+    if (discriminant < 0.0f) { BR(30); return 0; }
     const float sqrtDiscriminant = sqrtf(discriminant);
     float tLeft = -dotProduct - sqrtDiscriminant;
     float tRight = -dotProduct + sqrtDiscriminant;
@@ -368,24 +382,26 @@ static int linearProgram1(const Line *lines, int lineNo, float radius, V2 optVel
         const float denominator = det(lines[lineNo].direction, lines[i].direction);
         const float numerator = det(lines[i].direction, vsub(lines[lineNo].point, lines[i].point));
         if (fabsf(denominator) <= RVO_EPSILON) {
-            if (numerator < 0.0f) return 0;
+            if (numerator < 0.0f) { BR(31); return 0; }
+            BR(41);
             continue;
         }
         const float t = numerator / denominator;
         if (denominator >= 0.0f) tRight = fminf(tRight, t);
         else tLeft = fmaxf(tLeft, t);
-        if (tLeft > tRight) return 0;
+        if (tLeft > tRight) { BR(32); return 0; }
     }
     if (directionOpt) {
+        BR(38);
         if (vdot(optVelocity, lines[lineNo].direction) > 0.0f)
             *result = vadd(lines[lineNo].point, vscale(tRight, lines[lineNo].direction));
         else
             *result = vadd(lines[lineNo].point, vscale(tLeft, lines[lineNo].direction));
     } else {
         const float t = vdot(lines[lineNo].direction, vsub(optVelocity, lines[lineNo].point));
-        if (t < tLeft) *result = vadd(lines[lineNo].point, vscale(tLeft, lines[lineNo].direction));
-        else if (t > tRight) *result = vadd(lines[lineNo].point, vscale(tRight, lines[lineNo].direction));
-        else *result = vadd(lines[lineNo].point, vscale(t, lines[lineNo].direction));
+        if (t < tLeft) { BR(39); *result = vadd(lines[lineNo].point, vscale(tLeft, lines[lineNo].direction)); }
+        else if (t > tRight) { BR(40); *result = vadd(lines[lineNo].point, vscale(tRight, lines[lineNo].direction)); }
+        else { BR(42); *result = vadd(lines[lineNo].point, vscale(t, lines[lineNo].direction)); }
     }
     return 1;
 }
@@ -393,7 +409,7 @@ static int linearProgram1(const Line *lines, int lineNo, float radius, V2 optVel
 static int linearProgram2(const Line *lines, int n, float radius, V2 optVelocity, int directionOpt, V2 *result)
 {
     if (directionOpt) *result = vscale(radius, optVelocity); /* optVelocity * radius */
-    else if (absSq(optVelocity) > sqr(radius)) *result = vscale(radius, normalize(optVelocity));
+    else if (absSq(optVelocity) > sqr(radius)) { BR(33); *result = vscale(radius, normalize(optVelocity)); }
     else *result = optVelocity;
     for (int i = 0; i < n; ++i) {
         if (det(lines[i].direction, vsub(lines[i].point, *result)) > 0.0f) {
@@ -410,6 +426,7 @@ static int linearProgram2(const Line *lines, int n, float radius, V2 optVelocity
 static void linearProgram3(const Line *lines, int n, int numObstLines, int beginLine, float radius, V2 *result)
 {
     float distance = 0.0f;
+    BR(34);
     Line *projLines = (Line *)malloc(sizeof(Line) * (size_t)(n + 1));
     for (int i = beginLine; i < n; ++i) {
         if (det(lines[i].direction, vsub(lines[i].point, *result)) > distance) {
@@ -419,7 +436,8 @@ static void linearProgram3(const Line *lines, int n, int numObstLines, int begin
                 Line line;
                 const float determinant = det(lines[i].direction, lines[j].direction);
                 if (fabsf(determinant) <= RVO_EPSILON) {
-                    if (vdot(lines[i].direction, lines[j].direction) > 0.0f) continue;
+                    if (vdot(lines[i].direction, lines[j].direction) > 0.0f) { BR(35); continue; }
+                    BR(36);
                     line.point = vscale(0.5f, vadd(lines[i].point, lines[j].point));
                 } else {
                     line.point = vadd(lines[i].point,
@@ -430,8 +448,10 @@ static void linearProgram3(const Line *lines, int n, int numObstLines, int begin
                 projLines[np++] = line;
             }
             const V2 tempResult = *result;
-            if (linearProgram2(projLines, np, radius, v2(-lines[i].direction.y, lines[i].direction.x), 1, result) < np)
+            if (linearProgram2(projLines, np, radius, v2(-lines[i].direction.y, lines[i].direction.x), 1, result) < np) {
+                BR(37);
                 *result = tempResult;
+            }
             distance = det(lines[i].direction, vsub(lines[i].point, *result));
         }
     }
@@ -452,6 +472,7 @@ static void computeNewVelocity(RvoSim *s, int self)
 {
     Agent *a = &s->agents[self];
     a->nLines = 0;
+    g_br_on = (self == 0);
     const float invTimeHorizonObst = 1.0f / a->timeHorizonObst;
 
     for (int i = 0; i < a->nObstNb; ++i) {
@@ -467,6 +488,7 @@ static void computeNewVelocity(RvoSim *s, int self)
                 det(vsub(vscale(invTimeHorizonObst, relativePosition2), a->lines[j].point), a->lines[j].direction) -
                         invTimeHorizonObst * a->radius >= -RVO_EPSILON) {
                 alreadyCovered = 1;
+                BR(0);
                 break;
             }
         }
@@ -481,6 +503,7 @@ static void computeNewVelocity(RvoSim *s, int self)
         Line line;
 
         if (sP < 0.0f && distSq1 <= radiusSq) {
+            BR(1);
             if (s->obst[o1].isConvex) {
                 line.point = v2(0.0f, 0.0f);
                 line.direction = normalize(v2(-relativePosition1.y, relativePosition1.x));
@@ -488,6 +511,7 @@ static void computeNewVelocity(RvoSim *s, int self)
             }
             continue;
         } else if (sP > 1.0f && distSq2 <= radiusSq) {
+            BR(2);
             if (s->obst[o2].isConvex && det(relativePosition2, s->obst[o2].unitDir) >= 0.0f) {
                 line.point = v2(0.0f, 0.0f);
                 line.direction = normalize(v2(-relativePosition2.y, relativePosition2.x));
@@ -495,6 +519,7 @@ static void computeNewVelocity(RvoSim *s, int self)
             }
             continue;
         } else if (sP >= 0.0f && sP < 1.0f && distSqLine <= radiusSq) {
+            BR(3);
             line.point = v2(0.0f, 0.0f);
             line.direction = vneg(s->obst[o1].unitDir);
             pushLine(a, line);
@@ -503,7 +528,8 @@ static void computeNewVelocity(RvoSim *s, int self)
 
         V2 leftLegDirection, rightLegDirection;
         if (sP < 0.0f && distSqLine <= radiusSq) {
-            if (!s->obst[o1].isConvex) continue;
+            BR(4);
+            if (!s->obst[o1].isConvex) { BR(16); continue; }
             o2 = o1;
             const float leg1 = sqrtf(distSq1 - radiusSq);
             leftLegDirection = vdiv(v2(relativePosition1.x * leg1 - relativePosition1.y * a->radius,
@@ -511,7 +537,8 @@ static void computeNewVelocity(RvoSim *s, int self)
             rightLegDirection = vdiv(v2(relativePosition1.x * leg1 + relativePosition1.y * a->radius,
                                         -relativePosition1.x * a->radius + relativePosition1.y * leg1), distSq1);
         } else if (sP > 1.0f && distSqLine <= radiusSq) {
-            if (!s->obst[o2].isConvex) continue;
+            BR(5);
+            if (!s->obst[o2].isConvex) { BR(16); continue; }
             o1 = o2;
             const float leg2 = sqrtf(distSq2 - radiusSq);
             leftLegDirection = vdiv(v2(relativePosition2.x * leg2 - relativePosition2.y * a->radius,
@@ -519,6 +546,7 @@ static void computeNewVelocity(RvoSim *s, int self)
             rightLegDirection = vdiv(v2(relativePosition2.x * leg2 + relativePosition2.y * a->radius,
                                         -relativePosition2.x * a->radius + relativePosition2.y * leg2), distSq2);
         } else {
+            BR(6);
             if (s->obst[o1].isConvex) {
                 const float leg1 = sqrtf(distSq1 - radiusSq);
                 leftLegDirection = vdiv(v2(relativePosition1.x * leg1 - relativePosition1.y * a->radius,
@@ -540,10 +568,12 @@ static void computeNewVelocity(RvoSim *s, int self)
         if (s->obst[o1].isConvex && det(leftLegDirection, vneg(s->obst[leftNeighbor].unitDir)) >= 0.0f) {
             leftLegDirection = vneg(s->obst[leftNeighbor].unitDir);
             isLeftLegForeign = 1;
+            BR(7);
         }
         if (s->obst[o2].isConvex && det(rightLegDirection, s->obst[o2].unitDir) <= 0.0f) {
             rightLegDirection = s->obst[o2].unitDir;
             isRightLegForeign = 1;
+            BR(8);
         }
 
         const V2 leftCutoff = vscale(invTimeHorizonObst, vsub(s->obst[o1].point, a->position));
@@ -555,12 +585,14 @@ static void computeNewVelocity(RvoSim *s, int self)
         const float tRight = vdot(vsub(a->velocity, rightCutoff), rightLegDirection);
 
         if ((t < 0.0f && tLeft < 0.0f) || (o1 == o2 && tLeft < 0.0f && tRight < 0.0f)) {
+            BR(9);
             const V2 unitW = normalize(vsub(a->velocity, leftCutoff));
             line.direction = v2(unitW.y, -unitW.x);
             line.point = vadd(leftCutoff, vscale(a->radius * invTimeHorizonObst, unitW));
             pushLine(a, line);
             continue;
         } else if (t > 1.0f && tRight < 0.0f) {
+            BR(10);
             const V2 unitW = normalize(vsub(a->velocity, rightCutoff));
             line.direction = v2(unitW.y, -unitW.x);
             line.point = vadd(rightCutoff, vscale(a->radius * invTimeHorizonObst, unitW));
@@ -576,18 +608,21 @@ static void computeNewVelocity(RvoSim *s, int self)
                                    : absSq(vsub(a->velocity, vadd(rightCutoff, vscale(tRight, rightLegDirection)))));
 
         if (distSqCutoff <= distSqLeft && distSqCutoff <= distSqRight) {
+            BR(11);
             line.direction = vneg(s->obst[o1].unitDir);
             line.point = vadd(leftCutoff, vscale(a->radius * invTimeHorizonObst, v2(-line.direction.y, line.direction.x)));
             pushLine(a, line);
             continue;
         } else if (distSqLeft <= distSqRight) {
-            if (isLeftLegForeign) continue;
+            if (isLeftLegForeign) { BR(14); continue; }
+            BR(12);
             line.direction = leftLegDirection;
             line.point = vadd(leftCutoff, vscale(a->radius * invTimeHorizonObst, v2(-line.direction.y, line.direction.x)));
             pushLine(a, line);
             continue;
         } else {
-            if (isRightLegForeign) continue;
+            if (isRightLegForeign) { BR(15); continue; }
+            BR(13);
             line.direction = vneg(rightLegDirection);
             line.point = vadd(rightCutoff, vscale(a->radius * invTimeHorizonObst, v2(-line.direction.y, line.direction.x)));
             pushLine(a, line);
@@ -612,6 +647,7 @@ static void computeNewVelocity(RvoSim *s, int self)
             const float wLengthSq = absSq(w);
             const float dotProduct1 = vdot(w, relativePosition);
             if (dotProduct1 < 0.0f && sqr(dotProduct1) > combinedRadiusSq * wLengthSq) {
+                BR(20);
                 const float wLength = sqrtf(wLengthSq);
                 const V2 unitW = vdiv(w, wLength);
                 line.direction = v2(unitW.y, -unitW.x);
@@ -619,9 +655,11 @@ static void computeNewVelocity(RvoSim *s, int self)
             } else {
                 const float leg = sqrtf(distSq - combinedRadiusSq);
                 if (det(relativePosition, w) > 0.0f) {
+                    BR(21);
                     line.direction = vdiv(v2(relativePosition.x * leg - relativePosition.y * combinedRadius,
                                              relativePosition.x * combinedRadius + relativePosition.y * leg), distSq);
                 } else {
+                    BR(22);
                     line.direction = vneg(vdiv(v2(relativePosition.x * leg + relativePosition.y * combinedRadius,
                                                   -relativePosition.x * combinedRadius + relativePosition.y * leg), distSq));
                 }
@@ -629,6 +667,7 @@ static void computeNewVelocity(RvoSim *s, int self)
                 u = vsub(vscale(dotProduct2, line.direction), relativeVelocity);
             }
         } else {
+            BR(23);
             const float invTimeStep = 1.0f / s->timeStep;
             const V2 w = vsub(relativeVelocity, vscale(invTimeStep, relativePosition));
             const float wLength = vabs(w);

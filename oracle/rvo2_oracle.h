@@ -66,6 +66,9 @@ void rvo_get_agent_orca_line(const RvoSim *s, int i, int k, float *out4);
 /* out7 = point.x point.y unitDir.x unitDir.y next prev isConvex (as float) */
 void rvo_get_obstacle_vertex(const RvoSim *s, int i, float *out7);
 
+/* branch coverage counters (48 slots, ids in tests/orca_props.py BRANCHES); reset != 0 clears them after the read */
+void rvo_branch_counters(unsigned long long *out48, int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -241,8 +241,8 @@ def kde_topk(pos, k):
     """get_most_likely_samples on the device: pos [B,S,A,T,2] fp32 CUDA -> (sel [B,k] int32, logw [B,k] fp64)."""
     B, S, A, T, _ = pos.shape
     assert pos.is_cuda and pos.dtype == torch.float32 and pos.is_contiguous()
-    sel = torch.empty(B, k, dtype=torch.int32, device=pos.device)
-    lw = torch.empty(B, k, dtype=torch.float64, device=pos.device)
+    sel = torch.zeros(B, k, dtype=torch.int32, device=pos.device)   # zero-filled: a NaN total (singular covariance) leaves valid indices
+    lw = torch.zeros(B, k, dtype=torch.float64, device=pos.device)
     _capi.check(_capi.lib.snb_pred_kde_topk(_capi.ptr(pos), B, S, A, T, int(k), _capi.ptr(sel), _capi.ptr(lw), _capi.stream_ptr()),
                 "snb_pred_kde_topk")
     return sel, lw

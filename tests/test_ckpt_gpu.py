@@ -138,7 +138,13 @@ def test_kde_topk_path_with_shipped_checkpoint(tag):
     ref_fc, ref_lw = G[tag + "_forecasts"], G[tag + "_logw"]
     assert fc.shape[1:] == ref_fc.shape
     assert np.array_equal(fc[0][ids_out], ref_fc[ids_out])
-    assert np.max(np.abs(lw[0] - ref_lw)) <= 2e-2, np.max(np.abs(lw[0] - ref_lw))
+    # The KDE bandwidth is 0.01 .. 0.1 m (mid_sim_wrapper.py:60-62): position differences of a few mm between the bf16 denoiser and
+    # the fp32 reference move the per-sample log-likelihoods by O(0.1).  Tolerance on the (ascending) log-weights: 0.15; they stay
+    # normalised and sorted.  (precision="fp32x" tightens this, see test_fp32x_gpu.py.)
+    lw_err = np.max(np.abs(lw[0] - ref_lw))
+    _record(f"kde_logw_{tag}", lw_err)
+    assert lw_err <= 0.15, lw_err
+    assert np.all(np.diff(lw[0][ids_in[0]]) >= -1e-6) and abs(np.exp(lw[0][ids_in[0]]).sum() - 1.0) <= 1e-5
     worst = 0.0
     for j in range(n_ret):
         d = np.abs(fc_all[0][ids_in] - ref_fc[ids_in][:, j:j + 1]).max(axis=(0, 2, 3))
@@ -185,8 +191,12 @@ def test_reference_literal_constructor_call(tmp_path, monkeypatch):
     assert np.max(np.abs(fc - C4[tag + "_forecasts"])) <= 2e-2 and np.array_equal(lw, C4[tag + "_logw"])
     allf = sim.predict(noise=nz)
     assert allf.shape == (H, n_draw, 9, 2) and np.array_equal(allf, fc)      # k = S here: predict() returns every drawn sample
-    top, w = sim.get_most_likely_samples(torch.from_numpy(C4[tag + "_vel"]))
-    assert tuple(top.shape) == (H, n_ret, 8, 2) and tuple(w.shape) == (H, n_ret)
+    sim.num_ret_samples = 8                                       # the method form of the KDE top-k (mid_sim_wrapper.py:440-441)
+    pos2 = torch.from_numpy(np.ascontiguousarray(np.cumsum(C4[tag + "_vel"][:, :2], axis=2) * 0.25))
+    top, w = sim.get_most_likely_samples(pos2)
+    assert tuple(top.shape) == (2, 8, 8, 2) and tuple(w.shape) == (2, 8) and abs(float(w[0].exp().sum()) - 1.0) < 1e-4
+    flat = pos2.reshape(n_draw, -1)
+    assert all(bool((flat == top[:, j].reshape(1, -1)).all(1).any()) for j in range(8))     # the kept ones are drawn samples
 
 
 def test_step_size_must_divide_the_diffusion_steps():

@@ -298,3 +298,93 @@ def test_drop_in_forecaster_sim_class():
     assert fc.dtype == np.float64 and fc.shape == (H, n_ret, 9, 2) and lw.shape == (H, n_ret)
     assert np.max(np.abs(fc - G[tag + "_forecasts"])) <= 2e-2
     assert np.array_equal(lw, G[tag + "_logw"])
+
+
+IG = np.load(f"{GOLDEN}/ingest_cases.npz")
+
+
+@pytest.mark.parametrize("tag", ["jmid_h10_k20", "jmid_h3_k15", "imid_h5_k8"])
+def test_mpc_state_vector_matches_reference_function(tag):
+    """snb_pred_mpc_pack vs the output of the reference's own convert_to_mpc_state_vector (sicnav_acados.py:222-289, executed by
+    oracle/gen_golden.py ingest): bit-exact except sin / cos of the heading (CUDA libm vs glibc: <= 1 ulp)."""
+    from snb import _capi
+    joint = bool(IG[tag + "_joint"])
+    humans, goals, w = IG[tag + "_humans"], IG[tag + "_goals"], IG[tag + "_weights"]
+    H, k = humans.shape[0], w.shape[-1]
+    B = 3
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(np.broadcast_to(a, (B,) + a.shape))).cuda()
+    nx = 10 + (6 * H + k if joint else (6 + k) * H)
+    state = torch.zeros(B, nx, dtype=torch.float64, device="cuda"); theta = torch.zeros(B, H, dtype=torch.float64, device="cuda")
+    _capi.check(_capi.lib.snb_pred_mpc_pack(_capi.ptr(dev(IG[tag + "_robot"])), _capi.ptr(dev(humans)), _capi.ptr(dev(goals)), _capi.ptr(dev(w)),
+                                            None, None, None, B, H, k, 8, 4, int(joint), 0, 0, _capi.ptr(state), _capi.ptr(theta), None,
+                                            _capi.stream_ptr()), "mpc_pack")
+    ref = IG[tag + "_val"]
+    got = state.cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(np.delete(got[b], [2, 3]), np.delete(ref, [2, 3]))
+        assert np.max(np.abs(got[b][2:4] - ref[2:4])) <= 2.3e-16
+    _, th = PO.mpc_state_vector(IG[tag + "_robot"], humans, goals, w, joint)
+    assert np.max(np.abs(theta.cpu().numpy()[0] - th)) <= 4.5e-16 and theta[0, 1].item() == 0.0
+
+
+def test_stage_parameter_packing_is_bit_exact():
+    """Per-stage solver parameters (sicnav_acados.py:1389-1413) from the device-resident ingest outputs, vs the oracle restatement."""
+    B, H, S, horiz = 4, 6, 20, 4
+    hist, rh = random_histories(B, H, seed=33)
+    f = forecaster("rand", B, H, S=S, step=2)
+    f.set_history(torch.from_numpy(hist).cuda(), torch.from_numpy(rh).cuda())
+    fc, lw = f.predict(B)
+    resh, wts, goals, vpref = f.ingest(fc, lw, horiz=horiz)
+    rng = np.random.default_rng(1)
+    robot = rng.uniform(-2, 2, (B, 9)); humans = rng.uniform(-2, 2, (B, H, 4)); prefix = rng.normal(size=(B, horiz + 1, 11)); stat = rng.normal(size=(3, 4))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    state, theta, params = f.mpc_pack(t(robot), t(humans), goals, wts, resh=resh, horiz=horiz, stage_prefix=t(prefix), static_obs=t(stat))
+    state, theta, params = state.cpu().numpy(), theta.cpu().numpy(), params.cpu().numpy()
+    resh_h, w_h, g_h = resh.cpu().numpy(), wts.cpu().numpy(), goals.cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(params[b], PO.stage_params(resh_h[b], horiz, prefix[b], stat))
+        v, th = PO.mpc_state_vector(robot[b], humans[b], g_h[b], w_h[b], joint=True)
+        assert np.array_equal(np.delete(state[b], [2, 3]), np.delete(v, [2, 3])) and np.max(np.abs(state[b][2:4] - v[2:4])) <= 2.3e-16
+    # without prefix / static obstacles, and the horizon check (forecasts_reshaped keeps horiz+1 <= T frames)
+    _, _, p2 = f.mpc_pack(t(robot), t(humans), goals, wts, resh=resh, horiz=horiz)
+    assert np.array_equal(p2.cpu().numpy()[1], PO.stage_params(resh_h[1], horiz))
+
+
+def test_history_bootstrap_from_the_environment_state_log():
+    """reset_scenario_values (sicnav_acados.py:1163-1182): after reset with starts_moving = 10 the forecaster rings are filled from
+    env.states[-7:-1]; the environment keeps that log on the device (snb_env_log_push, crowd_sim_plus.py:1175-1181)."""
+    import bench
+    from snb.env import CrowdSimPlusBatch
+    B, H = 5, 4
+    cfg = configparser.RawConfigParser()
+    cfg.read_string(bench.ENV_CFG.format(H=H))
+    env = CrowdSimPlusBatch(B, "cuda")
+    env.configure(cfg)
+    env.freeze_done = False
+    log = []
+    real_launch = env._launch
+
+    def spy(action, active, *a, **k):           # records what the reference's self.states.append would hold: positions BEFORE the step
+        s = env.state
+        log.append(np.concatenate([np.stack([s.px.cpu().numpy(), s.py.cpu().numpy()], -1),
+                                   np.stack([s.rpx.cpu().numpy(), s.rpy.cpu().numpy()], -1)[:, None]], 1))
+        return real_launch(action, active, *a, **k)
+    env._launch = spy
+    env.reset('test', test_cases=np.arange(B))
+    act = torch.zeros(B, 2, dtype=torch.float64, device="cuda"); act[:, 1] = 0.7
+    for _ in range(3):
+        env.step(act)
+    assert env.n_logged == len(log) == 13
+    f = forecaster("rand", B, H, S=4, step=2)
+    f.reset_history()
+    f.bootstrap_history(env.state_log, (env.n_logged - 1) % env.LOG_DEPTH)
+    _, n1, p1, _ = f.encode(B)
+    c1 = f.encode(B)[0].clone()
+    for b in range(B):
+        hist_b, rob_b = PO.bootstrap_history([l[b] for l in log])
+        if b == 0:
+            hist_all = np.zeros((B, H, 6, 2)); rob_all = np.zeros((B, 6, 2))
+        hist_all[b], rob_all[b] = hist_b, rob_b
+    f.set_history(torch.from_numpy(hist_all).cuda(), torch.from_numpy(rob_all).cuda())
+    c2, n2, p2, _ = f.encode(B)
+    assert torch.equal(n1, n2) and torch.equal(p1, p2) and torch.equal(c1, c2)

@@ -60,3 +60,33 @@ def test_mpc_ingest_layout():
     for h in range(fc.shape[0]):
         assert goals[h, 0] == np.mean(f[h, :, 0, 0]) and goals[h, 1] == np.mean(f[h, :, 0, 1])
         assert vpref[h] == np.max(np.linalg.norm(np.diff(f[h], axis=1), axis=2) / 0.25)
+
+
+IG = np.load(f"{GOLDEN}/ingest_cases.npz")
+
+
+@pytest.mark.parametrize("tag", ["jmid_h10_k20", "jmid_h3_k15", "imid_h5_k8"])
+def test_mpc_state_vector_matches_reference_function(tag):
+    """ingest_cases.npz holds outputs of the reference's own convert_to_mpc_state_vector (source cut out of sicnav_acados.py:222-289
+    and executed, oracle/gen_golden.py ingest)."""
+    val, theta = PO.mpc_state_vector(IG[tag + "_robot"], IG[tag + "_humans"], IG[tag + "_goals"], IG[tag + "_weights"],
+                                     joint=bool(IG[tag + "_joint"]))
+    assert np.array_equal(val, IG[tag + "_val"])
+    assert theta[1] == 0.0 and np.all(np.isfinite(theta))
+
+
+def test_stage_params_and_bootstrap_layout():
+    rng = np.random.default_rng(3)
+    H, k, horiz = 4, 3, 4
+    resh = rng.normal(size=(horiz + 1, H * k, 2)); prefix = rng.normal(size=(horiz + 1, 7)); stat = rng.normal(size=(2, 4))
+    p = PO.stage_params(resh, horiz, prefix, stat)
+    assert p.shape == (horiz + 1, 7 + 4 * H * k + 8)
+    for idx in range(horiz + 1):
+        t = min(idx, horiz - 1)
+        ref = np.hstack([prefix[idx], resh[t, :, 0], resh[t, :, 1], resh[t + 1, :, 0], resh[t + 1, :, 1], stat.reshape(-1)])
+        assert np.array_equal(p[idx], ref)
+    states = [rng.normal(size=(H + 1, 2)) for _ in range(10)]
+    hist, rob = PO.bootstrap_history(states)
+    assert np.array_equal(hist[:, 0], states[-7][:H]) and np.array_equal(hist[:, -1], states[-2][:H]) and np.array_equal(rob[-1], states[-2][H])
+    with pytest.raises(IndexError):
+        PO.bootstrap_history(states[:6])
