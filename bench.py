@@ -160,7 +160,9 @@ def run_ours(args):
     env = CrowdSimPlusBatch(B, dev)
     env.configure(cfg)
     env.freeze_done = False                      # steady-state throughput: every env steps every iteration
-    env.reset('test', test_cases=(rank * B + np.arange(B)) % 500)
+    from snb.dist import global_case_ids
+    from snb.rollout import LinearRobot
+    env.reset('test', test_cases=global_case_ids(world * B, rank, world, test_size=500))   # case = global env id % test_size
     enc_w, ddpm_w, weights_desc = load_weights(args.synthetic_weights)
     fc_ = ForecasterBatch(enc_w, ddpm_w, max_envs=B, H=H, num_samples=S, step_size=NS, horizon=T,
                           joint=True, dt=0.25, radius=args.attention_radius, device=dev, seed=1234 + rank)
@@ -170,9 +172,8 @@ def run_ours(args):
     st = env.state
     out_bufs = (torch.zeros(B, H, S, T + 1, 2, dtype=torch.float64, device=dev), torch.zeros(B, H, S, dtype=torch.float64, device=dev))
 
-    def robot_action():                          # stand-in robot policy (Linear): the Acados MPC is CPU code, out of scope
-        d = torch.stack([st.rgx - st.rpx, st.rgy - st.rpy], 1)
-        return (d / d.norm(dim=1, keepdim=True).clamp_min(1e-9) * env.robot_v_pref).contiguous()
+    robot = LinearRobot(env)                     # stand-in robot policy (Linear, one libsnb launch): the Acados MPC is CPU code, out of scope
+    robot_action = robot.act
 
     def step(i):
         env.step(robot_action())
@@ -311,6 +312,131 @@ def run_ours(args):
                           f"{pk['tf_sustained'] * 1e12 / (den.flops_per_iter() * NS):.0f} env-steps/s per GPU (BASELINE.md section 3)",
         }
         _emit(out)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def _dist_setup():
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_stream(torch.cuda.Stream(dev))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    return rank, world, dev, dist
+
+
+def run_episode_mode(args):
+    """BASELINE configs[4]: `--envs` episodes per GPU run to done / time limit (snb/rollout.py), sharded over the ranks by global case
+    id, JMID prediction + MPC ingest before every robot action unless --no-predict; one NCCL all_gather of the metric matrix."""
+    import configparser
+    from snb import _capi, rollout
+    from snb.env import CrowdSimPlusBatch
+    from snb.jmid.forecaster import ForecasterBatch
+    rank, world, dev, dist = _dist_setup()
+    B, H, S, NS = args.envs, args.humans, args.samples, args.denoise_steps
+    cfg = configparser.RawConfigParser()
+    cfg.read_string(ENV_CFG.format(H=H))
+
+    def factory(n):
+        env = CrowdSimPlusBatch(n, dev)
+        env.configure(cfg)
+        return env
+    fc_, wdesc = None, "no predictor"
+    if not args.no_predict:
+        enc_w, ddpm_w, wdesc = load_weights(args.synthetic_weights)
+        fc_ = ForecasterBatch(enc_w, ddpm_w, max_envs=B, H=H, num_samples=S, step_size=NS, horizon=8, joint=True, dt=0.25,
+                              radius=args.attention_radius, device=dev, seed=1234 + rank)
+        if args.attention_radius != 3.0:
+            fc_.set_position_std(3.0)
+    total = world * B
+    for _ in range(1):                              # warm-up episode block: 2 steps (graph capture, allocator)
+        rollout.run_episodes(factory(B), rollout.global_case_ids(total, rank, world), forecaster=fc_, max_steps=2)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    l0 = _capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    summ, allm, stats = rollout.run_sharded(factory, total, rank, world, forecaster=fc_)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    tot = torch.tensor([ms, float(stats["env_steps"])], device=dev, dtype=torch.float64)
+    if dist is not None:
+        mx = tot.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tot.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, env_steps = float(mx[0].item()), float(sm[1].item())
+    else:
+        env_steps = float(tot[1].item())
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        _emit({"metric": "env-steps/s, full episode rollout to done (configs[4])", "value": env_steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+               "steps": stats["steps"], "warmup": 2, "ms_per_step": ms / max(1, stats["steps"]), "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "bf16" if fc_ is not None else "f32/f64", "mode": "episode",
+               "data": "synthetic: seeded circle-crossing test cases (global env id % 500), " + wdesc,
+               "config": {"workload": f"configs[4]: {total} episodes ({B} per GPU), ORCA x {H} humans, Linear robot stand-in, "
+                                      + (f"JMID {S} samples x {NS} DDIM iterations + MPC ingest before every action" if fc_ is not None else "simulator only"),
+                          "envs_per_gpu": B, "episodes": total, "env_steps": env_steps},
+               "episode_metrics": summ, "gpu_launches": int(_capi.launch_count() - l0), "clocks": clocks,
+               "collective": "one all_gather of the [B,9] fp64 metric matrix per rank at episode end (NCCL)" if dist is not None else None})
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_denoise_only(args):
+    """BASELINE configs[3]: the JMID denoise alone, 256 envs x 10 humans x 20 samples, 20 DDIM iterations: env-predictions/s."""
+    from snb import _capi
+    from snb.jmid import JmidDenoiser
+    rank, world, dev, dist = _dist_setup()
+    B = 256 if args.envs == 1024 else args.envs
+    A, S, T, NS = args.humans, args.samples, 8, args.denoise_steps
+    _, ddpm_w, wdesc = load_weights(args.synthetic_weights)
+    den = JmidDenoiser(ddpm_w, max_envs=B, A=A, S=S, T=T, joint=True, device=dev)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ctx = torch.randn(B, A, 256, device=dev, generator=g) * 0.3
+    xT = torch.randn(B, S * A, T, 2, device=dev, generator=g)
+    out = torch.empty(B, S, A, T, 2, device=dev)
+    for _ in range(max(3, args.warmup)):
+        den.denoise(ctx, xT, n_steps=NS, out=out)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    l0 = _capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        den.denoise(ctx, xT, n_steps=NS, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    pk = peaks()
+    if rank == 0:
+        val = world * B * args.steps / (ms / 1e3)
+        fl = den.flops_per_iter() * NS
+        _emit({"metric": "env-predictions/s, JMID 20-step denoise (configs[3])", "value": val, "unit": "env-predictions/s", "n_gpus": world,
+               "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "bf16", "mode": "denoise_only", "data": "synthetic ctx ~ 0.3 N(0,1), x_T ~ N(0,1); weights: " + wdesc,
+               "config": {"workload": f"configs[3]: {B} envs x {A} humans x {S} samples x {T} steps = {A * S * T} tokens/env, {NS} DDIM iterations, per GPU",
+                          "l2_policy": "inputs larger than L2 (activations of one chunk >> 126 MB)"},
+               "gpu_launches": int(_capi.launch_count() - l0), "clocks": clocks,
+               "roofline": {"bound": "tensor", "achieved": val / world * fl / 1e12, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                            "frac": val / world * fl / 1e12 / pk["tf_sustained"], "traffic": None,
+                            "note": "whole denoise loop against the sustained bf16 peak; algorithmic FLOPs per env-prediction = "
+                                    f"{fl / 1e9:.1f} GFLOP (BASELINE.md section 3)"}})
     if dist is not None:
         dist.destroy_process_group()
 
@@ -534,8 +660,16 @@ if __name__ == "__main__":
     ap.add_argument("--attention-radius", type=float, default=1e6,
                     help="attention / cluster radius of the predictor; 1e6 = every human inside the cluster (A = H, the metric's workload), "
                          "3.0 = the shipped value")
+    ap.add_argument("--mode", default="step", choices=["step", "episode", "denoise_only"],
+                    help="step (default): the BASELINE metric; episode: configs[4], full episodes to done, sharded by global case id; "
+                         "denoise_only: configs[3], the 20-step JMID denoise alone (env-predictions/s)")
+    ap.add_argument("--no-predict", action="store_true", help="episode mode: simulator only (no JMID prediction before each action)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.mode == "episode":
+        run_episode_mode(a)
+    elif a.mode == "denoise_only":
+        run_denoise_only(a)
     else:
         run_ours(a)

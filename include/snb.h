@@ -181,6 +181,19 @@ int snb_policy_predict_host(const SnbPolicyCfg *cfg, const double *self8_host, i
                             double *out_v2_host, int32_t *nbr_ids_host /* [max_neighbors] ob indices, may be NULL */,
                             int32_t *n_nbr_host);
 
+/*
+ * Episode rollout glue (the test loop of simple_test.py:216-269 around CrowdSimPlus.step), device-resident:
+ *   snb_robot_linear_action      the Linear robot policy (crowd_sim_plus/envs/policy/linear.py:16-23): action_dev [B,2] = v_pref * unit
+ *                                vector from the robot (extra 0) to its goal.  Stand-in for the MPC solve, which is CPU code.
+ *   snb_episode_metrics_update   per-environment episode counters from one step's flags / dmin (what simple_test.py accumulates from
+ *                                `info`, :232-258, and pickles, :306-319): metrics_dev [B,9] fp64 = success, timeout, n_steps, nav_time,
+ *                                n_collisions, n_wall_collisions, n_frozen, n_too_close, min_dist; live_dev [B] uint8 is cleared when an
+ *                                environment reports SNB_F_DONE (finished environments stop counting).
+ */
+int snb_robot_linear_action(const SnbCrowdState *state, double v_pref, double *action_dev, void *stream);
+int snb_episode_metrics_update(double *metrics_dev, uint8_t *live_dev, const int32_t *flags_dev, const double *dmin_dev,
+                               double time_step, int32_t B, void *stream);
+
 /* ======================================================================================================
  * JMID / iMID denoiser  (sicnav_diffusion/JMID/MID/models/diffusion.py:153-209, 478-541)
  * ====================================================================================================== */

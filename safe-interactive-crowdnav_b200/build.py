@@ -31,6 +31,7 @@ UNITS = [
     ("pred_encode.cu", []),
     ("pred_post.cu", []),
     ("pred_api.cu", []),
+    ("rollout_kernels.cu", ["-fmad=false"]),
 ]
 
 

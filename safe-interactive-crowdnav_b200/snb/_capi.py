@@ -112,6 +112,8 @@ _proto("snb_env_whatif", C.c_int, [C.POINTER(PolicyCfg), C.POINTER(DoorCfg), C.P
                                     _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp])
 _proto("snb_policy_predict_host", C.c_int, [C.POINTER(PolicyCfg), C.POINTER(_d), _i32, C.POINTER(_d), _i32, C.POINTER(_d),
                                              C.POINTER(_d), C.POINTER(_i32), C.POINTER(_i32)])
+_proto("snb_robot_linear_action", C.c_int, [C.POINTER(CrowdState), _d, _vp, _vp])
+_proto("snb_episode_metrics_update", C.c_int, [_vp, _vp, _vp, _vp, _d, _i32, _vp])
 _proto("snb_jmid_create", C.c_int, [C.POINTER(_vp), C.POINTER(JmidWeights), _i32, _i32, _i32, _i32, _i32, _vp], required=False)
 _proto("snb_jmid_destroy", C.c_int, [_vp], required=False)
 _proto("snb_jmid_denoise", C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp], required=False)

@@ -114,13 +114,13 @@ class CrowdSimPlusBatch:
                                progress_factor=r.get("progress_factor", 0.0), time_limit=self.time_limit)
 
     # ------------------------------------------------------------------ reset
-    def reset(self, phase='test', test_cases=None, on_device=True):
+    def reset(self, phase='test', test_cases=None):
         """Builds env b from test case `test_cases[b]` (default b) with the reference's seeding
         (default_rng(offset + case), crowd_sim_plus.py:658-664), runs the `starts_moving` warm-up steps with a zero robot
         action (:709-720).  Returns the observation dict.
-        on_device (default): the scenes are generated by snb_scene_reset, one thread per environment consuming the same
-        PCG64 stream; on_device=False runs the host restatement (snb/scenario.py) and uploads -- same draws, same accept /
-        reject decisions, positions equal to the last ulp of cos / sin / atan2.  The debug layout (case -1) is host only."""
+        The scenes are generated by snb_scene_reset, one thread per environment consuming the PCG64 stream of numpy's
+        default_rng in the reference's draw order.  test_cases[0] == -1 selects the reference's fixed 3-human debug layout
+        (:676-682) for every environment."""
         assert phase in ('train', 'val', 'test')
         self.phase = phase
         self.sim_env = self.test_sim if phase == 'test' else self.train_val_sim
@@ -144,7 +144,7 @@ class CrowdSimPlusBatch:
         # the reference builds fresh Human / policy objects on every reset, so is_bottleneck starts False each time (:448-449)
         if hasattr(self.human_policy, 'is_bottleneck') or pol_name == 'sfm':
             self.human_policy.is_bottleneck = bool(self.sim_env == 'hallway_bottleneck' and pol_name == 'sfm')
-        if on_device and not debug_case:
+        if not debug_case:
             cap = {'val': self.case_capacity['val'], 'test': self.case_capacity['test']}
             offset = {"train": cap["val"] + cap["test"], "val": 0, "test": cap["val"]}[phase]
             seeds = torch.from_numpy((cases.astype(np.int64) + offset).astype(np.uint64).view(np.int64)).to(self.device)
@@ -161,12 +161,12 @@ class CrowdSimPlusBatch:
             if int(self.reset_draws.min().item()) < 0:
                 raise _capi.SnbError("scene reset: rejection sampling gave up (over-crowded scene: too many humans for this layout)")
         else:
-            hum = np.zeros((self.B, H, 8))
-            for b, case in enumerate(cases):
-                sc = scenario.generate_scene(self.sim_env, H, int(case), phase, p, {'val': self.case_capacity['val'], 'test': self.case_capacity['test']})
-                hum[b] = sc["humans"]
-            st.load_numpy(px=hum[:, :, 0], py=hum[:, :, 1], gx=hum[:, :, 2], gy=hum[:, :, 3], fgx=hum[:, :, 4], fgy=hum[:, :, 5],
-                          vpref=hum[:, :, 6], theta=hum[:, :, 7], radius=np.full((self.B, H), self.human_radius))
+            if self._door_cfg().enabled:
+                raise NotImplementedError("the debug layout (test case -1) is only built for rules without a door goal")
+            lay = scenario.debug_layout(p)          # px, py, gx, gy, v_pref, theta
+            rep = lambda c: np.broadcast_to(lay[:, c], (self.B, H))
+            st.load_numpy(px=rep(0), py=rep(1), gx=rep(2), gy=rep(3), fgx=rep(2), fgy=rep(3), vpref=rep(4), theta=rep(5),
+                          radius=np.full((self.B, H), self.human_radius))
             st.ex_px.fill_(0.0); st.ex_py.fill_(-self.circle_radius); st.ex_radius.fill_(self.robot_radius)
             st.rgx.fill_(0.0); st.rgy.fill_(self.circle_radius); st.rtheta.fill_(np.pi / 2)
         self.state = st

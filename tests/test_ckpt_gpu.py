@@ -196,7 +196,7 @@ def test_reference_literal_constructor_call(tmp_path, monkeypatch):
     top, w = sim.get_most_likely_samples(pos2)
     assert tuple(top.shape) == (2, 8, 8, 2) and tuple(w.shape) == (2, 8) and abs(float(w[0].exp().sum()) - 1.0) < 1e-4
     flat = pos2.reshape(n_draw, -1)
-    assert all(bool((flat == top[:, j].reshape(1, -1)).all(1).any()) for j in range(8))     # the kept ones are drawn samples
+    assert all(bool((flat == top[:, j].cpu().reshape(1, -1)).all(1).any()) for j in range(8))     # the kept ones are drawn samples
 
 
 def test_step_size_must_divide_the_diffusion_steps():

@@ -450,10 +450,10 @@ class _CountingRng:
                                       ("rectangle", 6, 128)])
 def test_scene_reset_on_device_matches_host_generator(rule, H, B):
     """snb_scene_reset (SeedSequence + PCG64 + the reference's rejection sampling, one thread per environment) against the host
-    restatement of CrowdSimPlus.reset (snb/scenario.py, pinned to reference episodes): same number of draws per environment (=
+    restatement of CrowdSimPlus.reset (oracle/scenario_oracle.py, pinned to reference episodes): same number of draws per environment (=
     identical accept / reject sequence), v_pref bit-equal (pure PCG64 arithmetic), positions / goals within 1e-12 (libm ulps)."""
     import configparser
-    from snb import scenario
+    import scenario_oracle as scenario
     from snb.env import CrowdSimPlusBatch
     cfg = configparser.RawConfigParser()
     cfg.read_string(f"""
@@ -495,7 +495,7 @@ discomfort_penalty_factor = 0.5
     env = CrowdSimPlusBatch(B, "cuda")
     env.configure(cfg)
     cases = (np.arange(B) * 7 + 3) % 500
-    env.reset('test', test_cases=cases, on_device=True)
+    env.reset('test', test_cases=cases)
     torch.cuda.synchronize()
     dev = env.state.to_numpy("px", "py", "gx", "gy", "fgx", "fgy", "vpref", "theta", "radius", "ex_px", "ex_py", "rgx", "rgy", "rtheta", "prev_dist")
     draws = env.reset_draws.cpu().numpy()
@@ -515,7 +515,10 @@ discomfort_penalty_factor = 0.5
     # and the simulator runs from the device-built scenes exactly as from the uploaded ones
     env2 = CrowdSimPlusBatch(B, "cuda")
     env2.configure(cfg)
-    env2.reset('test', test_cases=cases, on_device=False)
+    env2.reset('test', test_cases=cases)
+    hum = np.stack([scenario.generate_scene(rule, H, int(c), 'test', p)["humans"] for c in cases])     # host-generated scenes, uploaded
+    env2.state.load_numpy(px=hum[..., 0], py=hum[..., 1], gx=hum[..., 2], gy=hum[..., 3], fgx=hum[..., 4], fgy=hum[..., 5],
+                          vpref=hum[..., 6], theta=hum[..., 7])
     a = torch.zeros(B, 2, dtype=torch.float64, device="cuda"); a[:, 1] = 1.0
     for _ in range(5):
         env.step(a); env2.step(a)

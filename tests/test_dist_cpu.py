@@ -82,3 +82,53 @@ def test_metric_gather_world2_equals_single_process():
     for rank, allm, summ in res:
         assert torch.equal(allm, single), rank
         assert 0.0 <= summ["success_rate"] <= 1.0 and summ["mean_steps"] > 0
+
+
+def _oracle_episode_metrics(cases):
+    """Real flag words: the CPU oracle (oracle/rollout_oracle.py) runs the ORCA episodes of `cases`; EpisodeMetrics consumes its per-step
+    flags / dmin exactly as snb/rollout.py feeds it the kernel's."""
+    for p in (os.path.join(ROOT, "safe-interactive-crowdnav_b200"), os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import numpy as np
+    import rollout_oracle as RO
+    from snb.dist import EpisodeMetrics
+    env, pcfg, dcfg, rcfg = RO.reset(cases, 5, time_limit=8.0, n_threads=1)
+    m_ref, trace = RO.run_episodes(env, pcfg, dcfg, rcfg, n_threads=1)
+    em = EpisodeMetrics(len(cases), "cpu", 0.25)
+    for flags, dmin, live in trace:
+        em.update(torch.from_numpy(np.where(live, flags, 0).astype(np.int32)), torch.from_numpy(dmin))
+    assert np.array_equal(em.m.numpy(), m_ref)
+    return em.m
+
+
+def _worker_real(rank, world, port, total, q):
+    sys.path.insert(0, os.path.join(ROOT, "safe-interactive-crowdnav_b200"))
+    from snb.dist import gather_metrics, global_case_ids, summarize
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    local = _oracle_episode_metrics(global_case_ids(total, rank, world, test_size=500))
+    allm = gather_metrics(local, total_envs=total)
+    q.put((rank, allm.clone(), summarize(allm)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_sharded_episode_metrics_world2_on_oracle_generated_flags():
+    """configs[4] host logic on REAL episodes: 25 ORCA test cases sharded 13 + 12 over two gloo ranks; the gathered metric matrix and
+    the summary equal a single-process run of all 25 cases (results do not depend on the number of ranks)."""
+    total, world = 25, 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_real, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=150) for _ in range(world)]
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    single = _oracle_episode_metrics(list(range(total)))
+    for rank, allm, summ in res:
+        assert torch.equal(allm, single), rank
+        assert summ["episodes"] == total and summ["success_rate"] + summ["timeout_rate"] == 1.0

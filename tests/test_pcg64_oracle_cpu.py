@@ -21,7 +21,7 @@ def test_state_and_stream_equal_numpy(seed):
 
 @pytest.mark.parametrize("rule,H", [("circle_crossing", 10), ("hallway", 6), ("hallway_static", 5), ("hallway_bottleneck", 5)])
 def test_scene_generator_on_the_restated_stream_equals_numpy_stream(rule, H):
-    from snb import scenario
+    import scenario_oracle as scenario
     p = scenario.SceneParams(4.0, 2.5, 4, 0.3, 1.5, 0.25, 0.2, True)
     segs, door = scenario.static_obstacles(rule, p)
     for case in (0, 7, 123):

@@ -315,7 +315,8 @@ def test_mpc_state_vector_matches_reference_function(tag):
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(np.broadcast_to(a, (B,) + a.shape))).cuda()
     nx = 10 + (6 * H + k if joint else (6 + k) * H)
     state = torch.zeros(B, nx, dtype=torch.float64, device="cuda"); theta = torch.zeros(B, H, dtype=torch.float64, device="cuda")
-    _capi.check(_capi.lib.snb_pred_mpc_pack(_capi.ptr(dev(IG[tag + "_robot"])), _capi.ptr(dev(humans)), _capi.ptr(dev(goals)), _capi.ptr(dev(w)),
+    t_r, t_h, t_g, t_w = dev(IG[tag + "_robot"]), dev(humans), dev(goals), dev(w)        # kept alive across the call
+    _capi.check(_capi.lib.snb_pred_mpc_pack(_capi.ptr(t_r), _capi.ptr(t_h), _capi.ptr(t_g), _capi.ptr(t_w),
                                             None, None, None, B, H, k, 8, 4, int(joint), 0, 0, _capi.ptr(state), _capi.ptr(theta), None,
                                             _capi.stream_ptr()), "mpc_pack")
     ref = IG[tag + "_val"]
