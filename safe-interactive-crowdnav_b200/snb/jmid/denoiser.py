@@ -137,6 +137,7 @@ class JmidDenoiser:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
-            _capi.lib.snb_jmid_destroy(h)
+        lib = getattr(_capi, "lib", None)      # None while the interpreter shuts down
+        if h and lib is not None:
+            lib.snb_jmid_destroy(h)
             self._h = None

@@ -232,8 +232,9 @@ class ForecasterBatch:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
-            _capi.lib.snb_pred_destroy(h)
+        lib = getattr(_capi, "lib", None)      # None while the interpreter shuts down
+        if h and lib is not None:
+            lib.snb_pred_destroy(h)
             self._h = None
 
 

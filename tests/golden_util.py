@@ -1,4 +1,5 @@
 """Helpers shared by the CPU (oracle) and GPU (CUDA path) golden-rollout tests."""
+import configparser
 import glob
 import os
 
@@ -27,3 +28,13 @@ def door_params(g):
     enabled = g["sim"] in DOOR_SIMS and len(g["segs"]) > 0
     d = np.nan_to_num(g["door"], nan=0.0)
     return (int(enabled),) + tuple(float(x) for x in d)
+
+
+def human_policy_config(g):
+    """the [env] / [humans] keys the human policies read in configure (orca_plus.py:15-27, social_force.py:21-36); values of the
+    reference's sicnav_diffusion/configs/env.config as the golden generator used them"""
+    cfg = configparser.RawConfigParser()
+    cfg.read_dict({"env": {"time_step": str(float(g["time_step"]))},
+                   "humans": {"radius": str(float(g["policy_radius"])), "safety_space": str(float(g["safety_space"])), "A": "3.0", "B": "0.18",
+                              "KI": "1.0", "A_static": "2.0", "B_static": "0.025", "A_bottleneck": "6.0", "B_bottleneck": "0.12"}})
+    return cfg
