@@ -239,6 +239,13 @@ int snb_jmid_denoise(SnbJmid *h, const float *ctx_dev, const float *x_T_dev, flo
  * (the predictor's attention cluster changes size from step to step, mid_sim_wrapper.py:322-355) */
 int snb_jmid_denoise_agents(SnbJmid *h, const float *ctx_dev, const float *x_T_dev, float *out_vel_dev, int32_t B, int32_t A,
                             int32_t n_steps, void *stream);
+/* Arithmetic of the noise network.  SNB_PREC_BF16 (default): bf16 tensor-core operands, fp32 accumulation / softmax / LayerNorm
+ * statistics / DDIM state.  SNB_PREC_FP32X: fp32-class -- fp32 activations, every nn.Linear as a split-bf16 (3 pieces, 6 partial
+ * products) tcgen05 GEMM accumulated in fp32, attention / LayerNorm / ConcatSquash in fp32 on the CUDA cores -- the instrument that
+ * separates rounding error from algorithmic error against the reference's fp32 torch path (models/diffusion.py:173-209); ~6x the
+ * tensor FLOPs, small chunks.  Buffers for it are allocated on the first switch. */
+enum { SNB_PREC_BF16 = 0, SNB_PREC_FP32X = 1 };
+int snb_jmid_set_precision(SnbJmid *h, int32_t precision, void *stream);
 /* sizes the handle was created with */
 int snb_jmid_dims(const SnbJmid *h, int32_t *A, int32_t *S, int32_t *T, int32_t *joint);
 

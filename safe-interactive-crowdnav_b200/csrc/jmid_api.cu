@@ -47,6 +47,12 @@ struct SnbJmid {
     std::map<int64_t, int> graph_uses;
     int use_graphs = 1;
     cudaStream_t own_stream = nullptr;
+    // precision "fp32x" (csrc/jmid_fp32x.cu): fp32 activations, weights split into 3 bf16 pieces laid out along K (K' = 6K)
+    int precision = SNB_PREC_BF16, x_chunk_envs = 0;
+    bf16 *x_wqkv[NL] = {}, *x_wo[NL] = {}, *x_w1[NL] = {}, *x_w2[NL] = {}, *x_wc3 = nullptr, *x_wc4 = nullptr, *x_a6 = nullptr;
+    float *x_h = nullptr, *x_y = nullptr, *x_qkv = nullptr, *x_att = nullptr, *x_ff = nullptr, *x_pre = nullptr, *x_t3 = nullptr, *x_t4 = nullptr;
+    const float *src_w[NL][4] = {}, *src_c3 = nullptr, *src_c4 = nullptr;   // caller's fp32 weights are copied at create (kept for the split)
+    std::map<std::pair<int, int>, Plans> x_plans;
     // host-call staging
     float *d_ctx = nullptr, *d_xT = nullptr, *d_p0 = nullptr, *d_vel = nullptr, *d_pos = nullptr;
 };
@@ -146,6 +152,99 @@ int net_forward(SnbJmid *h, Plans *P, const float *x_in, float *x_next, float *e
 
 } // namespace
 
+namespace {
+
+int get_x_plans(SnbJmid *h, int n_env, int A, Plans **out)
+{
+    const std::pair<int, int> key(n_env, A);
+    auto it = h->x_plans.find(key);
+    if (it != h->x_plans.end()) { *out = &it->second; return SNB_OK; }
+    Plans p;
+    p.n_env = n_env; p.A = A; p.N = A * h->S * h->T; p.M = n_env * p.N;
+    int rc = 0;
+    for (int l = 0; l < NL && !rc; ++l) {
+        rc = snb_gemm_plan(&p.qkv[l], h->x_a6, h->x_wqkv[l], h->x_qkv, 1, p.M, 3 * D, 6 * D);
+        if (!rc) rc = snb_gemm_plan(&p.out[l], h->x_a6, h->x_wo[l], h->x_pre, 1, p.M, D, 6 * D);
+        if (!rc) rc = snb_gemm_plan(&p.ff1[l], h->x_a6, h->x_w1[l], h->x_ff, 1, p.M, DFF, 6 * D);
+        if (!rc) rc = snb_gemm_plan(&p.ff2[l], h->x_a6, h->x_w2[l], h->x_pre, 1, p.M, D, 6 * DFF);
+    }
+    if (!rc) rc = snb_gemm_plan(&p.c3, h->x_a6, h->x_wc3, h->x_t3, 1, p.M, 256, 6 * D);
+    if (!rc) rc = snb_gemm_plan(&p.c4, h->x_a6, h->x_wc4, h->x_t4, 1, p.M, 128, 6 * 256);
+    if (rc) return rc;
+    h->x_plans[key] = p;
+    *out = &h->x_plans[key];
+    return SNB_OK;
+}
+
+// fp32-class forward (diffusion.py:173-209): same dataflow as net_forward, fp32 activations, split-bf16 GEMMs
+int net_forward_x(SnbJmid *h, Plans *P, const float *x_in, float *x_next, float *eps_out, int t, int t_next, cudaStream_t s)
+{
+    const int M = P->M, n_ba = P->n_env * P->A;
+    int rc = snb_k_hyper_iter(h->hyper, h->gc, h->bc, h->gate, h->hb, n_ba, h->betas[t], s);
+    if (rc) return rc;
+    if ((rc = snb_x_embed(x_in, h->c1_w, h->c1_b, h->gate, h->hb, h->pe, h->x_h, M, P->N, h->T, P->A, s))) return rc;
+    GemmEpi e;
+    auto gemm = [&](const GemmPlan *pl, const float *src, int K, int relu, const float *bias) -> int {
+        int r = snb_x_split3(src, h->x_a6, (size_t)M, K, 0, relu, s);
+        if (r) return r;
+        memset(&e, 0, sizeof(e));
+        e.bias = bias;
+        return snb_gemm_launch(pl, EPI_BIAS_F32, &e, h->num_sms, s);
+    };
+    for (int l = 0; l < NL; ++l) {
+        if ((rc = gemm(&P->qkv[l], h->x_h, D, 0, h->L[l].bqkv))) return rc;
+        if ((rc = h->joint ? snb_x_attention(h->x_qkv, h->x_att, P->n_env, P->N, s) : snb_x_attention(h->x_qkv, h->x_att, M / h->T, h->T, s))) return rc;
+        if ((rc = gemm(&P->out[l], h->x_att, D, 0, h->L[l].bo))) return rc;
+        if ((rc = snb_x_layernorm(h->x_pre, h->x_h, h->L[l].n1w, h->L[l].n1b, h->x_y, M, s))) return rc;
+        if ((rc = gemm(&P->ff1[l], h->x_y, D, 0, h->L[l].b1))) return rc;
+        if ((rc = gemm(&P->ff2[l], h->x_ff, DFF, 1, h->L[l].b2))) return rc;          // ReLU folded into the split of linear1's output
+        if ((rc = snb_x_layernorm(h->x_pre, h->x_y, h->L[l].n2w, h->L[l].n2b, h->x_h, M, s))) return rc;
+    }
+    if ((rc = gemm(&P->c3, h->x_h, D, 0, h->c3_b))) return rc;
+    if ((rc = snb_x_csl_apply(h->x_t3, h->gate + 512, h->hb + 512, (size_t)M, 256, P->N, h->T, P->A, s))) return rc;
+    if ((rc = gemm(&P->c4, h->x_t3, 256, 0, h->c4_b))) return rc;
+    if ((rc = snb_x_csl_apply(h->x_t4, h->gate + 768, h->hb + 768, (size_t)M, 128, P->N, h->T, P->A, s))) return rc;
+    const float ab = h->alpha_bars[t], abn = h->alpha_bars[t_next];
+    return snb_x_tail_ddim(h->x_t4, h->lin_w, h->lin_b, h->gate + 896, h->hb + 896, x_in, x_next, eps_out, M, P->N, h->T, P->A,
+                           sqrtf(1.0f - ab), sqrtf(ab), sqrtf(abn), sqrtf(1.0f - abn), s);
+}
+
+} // namespace
+
+extern "C" int snb_jmid_set_precision(SnbJmid *h, int32_t precision, void *stream)
+{
+    SNB_REQUIRE(h, SNB_EINVAL, "snb_jmid_set_precision: NULL handle");
+    SNB_REQUIRE(precision == SNB_PREC_BF16 || precision == SNB_PREC_FP32X, SNB_EINVAL, "snb_jmid_set_precision: unknown precision %d", precision);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (precision == SNB_PREC_FP32X && !h->x_a6) {
+        // first use: split the weights, allocate fp32 activations for a small chunk (this is a parity instrument: 12 KB of split
+        // operand per token row)
+        const char *ce = getenv("SNB_JMID_X_CHUNK");
+        int chunk = ce ? atoi(ce) : 8;
+        if (chunk < 1) chunk = 1;
+        h->x_chunk_envs = chunk < h->max_envs ? chunk : h->max_envs;
+        const size_t Mc = (((size_t)h->x_chunk_envs * h->N + 127) / 128) * 128;
+        int rc = 0;
+#define TRY(x) do { if (!rc) rc = (x); } while (0)
+        for (int l = 0; l < NL; ++l) {
+            TRY(dev_alloc(h, &h->x_wqkv[l], (size_t)3 * D * 6 * D)); TRY(dev_alloc(h, &h->x_wo[l], (size_t)D * 6 * D));
+            TRY(dev_alloc(h, &h->x_w1[l], (size_t)DFF * 6 * D)); TRY(dev_alloc(h, &h->x_w2[l], (size_t)D * 6 * DFF));
+            TRY(snb_x_split3(h->src_w[l][0], h->x_wqkv[l], 3 * D, D, 1, 0, s)); TRY(snb_x_split3(h->src_w[l][1], h->x_wo[l], D, D, 1, 0, s));
+            TRY(snb_x_split3(h->src_w[l][2], h->x_w1[l], DFF, D, 1, 0, s)); TRY(snb_x_split3(h->src_w[l][3], h->x_w2[l], D, DFF, 1, 0, s));
+        }
+        TRY(dev_alloc(h, &h->x_wc3, (size_t)256 * 6 * D)); TRY(dev_alloc(h, &h->x_wc4, (size_t)128 * 6 * 256));
+        TRY(snb_x_split3(h->src_c3, h->x_wc3, 256, D, 1, 0, s)); TRY(snb_x_split3(h->src_c4, h->x_wc4, 128, 256, 1, 0, s));
+        TRY(dev_alloc(h, &h->x_a6, Mc * 6 * DFF));
+        TRY(dev_alloc(h, &h->x_h, Mc * D)); TRY(dev_alloc(h, &h->x_y, Mc * D)); TRY(dev_alloc(h, &h->x_qkv, Mc * 3 * D));
+        TRY(dev_alloc(h, &h->x_att, Mc * D)); TRY(dev_alloc(h, &h->x_ff, Mc * DFF)); TRY(dev_alloc(h, &h->x_pre, Mc * D));
+        TRY(dev_alloc(h, &h->x_t3, Mc * 256)); TRY(dev_alloc(h, &h->x_t4, Mc * 128));
+#undef TRY
+        if (rc) return rc;
+    }
+    h->precision = precision;
+    return SNB_OK;
+}
+
 extern "C" double snb_jmid_flops_per_iter(int32_t A, int32_t S, int32_t T, int32_t joint)
 {
     const double N = (double)A * S * T, R = (double)A * S;
@@ -183,6 +282,11 @@ extern "C" int snb_jmid_create(SnbJmid **out, const SnbJmidWeights *w, int32_t m
     }
     TRY(dup_f32(h, &h->c1_w, (const float *)w->concat1.layer_w, 512 * 2, s));
     TRY(dup_f32(h, &h->c1_b, (const float *)w->concat1.layer_b, 512, s));
+    {
+        float *c3 = nullptr, *c4 = nullptr;
+        TRY(dup_f32(h, &c3, (const float *)w->concat3.layer_w, 256 * 512, s)); TRY(dup_f32(h, &c4, (const float *)w->concat4.layer_w, 128 * 256, s));
+        h->src_c3 = c3; h->src_c4 = c4;
+    }
     TRY(dup_bf16(h, &h->wc3, (const float *)w->concat3.layer_w, 256 * 512, s));
     TRY(dup_f32(h, &h->c3_b, (const float *)w->concat3.layer_b, 256, s));
     TRY(dup_bf16(h, &h->wc4, (const float *)w->concat4.layer_w, 128 * 256, s));
@@ -192,6 +296,12 @@ extern "C" int snb_jmid_create(SnbJmid **out, const SnbJmidWeights *w, int32_t m
     TRY(dup_f32(h, &h->pe, (const float *)w->pos_emb, (size_t)T * 512, s));
     for (int l = 0; l < NL; ++l) {
         const SnbEncLayerWeights &lw = w->layers[l];
+        {   // fp32 copies of the four matrices: the fp32x path splits them on first use (27 MB, only touched then)
+            float *c0 = nullptr, *c1 = nullptr, *c2 = nullptr, *c3 = nullptr;
+            TRY(dup_f32(h, &c0, (const float *)lw.in_proj_w, (size_t)3 * D * D, s)); TRY(dup_f32(h, &c1, (const float *)lw.out_proj_w, (size_t)D * D, s));
+            TRY(dup_f32(h, &c2, (const float *)lw.lin1_w, (size_t)DFF * D, s)); TRY(dup_f32(h, &c3, (const float *)lw.lin2_w, (size_t)D * DFF, s));
+            h->src_w[l][0] = c0; h->src_w[l][1] = c1; h->src_w[l][2] = c2; h->src_w[l][3] = c3;
+        }
         TRY(dup_bf16(h, &h->L[l].wqkv, (const float *)lw.in_proj_w, (size_t)3 * D * D, s));
         TRY(dup_f32(h, &h->L[l].bqkv, (const float *)lw.in_proj_b, 3 * D, s));
         TRY(dup_bf16(h, &h->L[l].wo, (const float *)lw.out_proj_w, (size_t)D * D, s));
@@ -259,7 +369,7 @@ int chunk_sequence(SnbJmid *h, Plans *P, int n_steps, cudaStream_t s, float **re
     if (rc) return rc;
     float *cur = h->xa, *nxt = h->xb;
     for (int t = 100; t > 0; t -= stride) {
-        if ((rc = net_forward(h, P, cur, nxt, nullptr, t, t - stride, s))) return rc;
+        if ((rc = (h->precision == SNB_PREC_FP32X ? net_forward_x : net_forward)(h, P, cur, nxt, nullptr, t, t - stride, s))) return rc;
         float *tmp = cur; cur = nxt; nxt = tmp;
     }
     *result = cur;
@@ -281,24 +391,25 @@ extern "C" int snb_jmid_denoise_agents(SnbJmid *h, const float *ctx, const float
                 "(the reference raises KeyError: 0 on traj[0])", n_steps, n_steps, stride);
     const int n_iter = (100 + stride - 1) / stride;
     const int N = A * h->S * h->T;
+    const bool fx = h->precision == SNB_PREC_FP32X;
     // a chunk is bounded by ROWS (chunk_envs * tokens at full A): fewer agents per env -> more envs per chunk
-    int chunk = (int)(((size_t)h->chunk_envs * h->N) / N);
+    int chunk = (int)(((size_t)(fx ? h->x_chunk_envs : h->chunk_envs) * h->N) / N);
     if (chunk < 1) chunk = 1;
     for (int e0 = 0; e0 < B; e0 += chunk) {
         const int ne = (B - e0) < chunk ? (B - e0) : chunk;
         Plans *P = nullptr;
-        int rc = get_plans(h, ne, A, &P);
+        int rc = fx ? get_x_plans(h, ne, A, &P) : get_plans(h, ne, A, &P);
         if (rc) return rc;
         const size_t M = (size_t)P->M;
         SNB_CUDA_TRY(cudaMemcpyAsync(h->ctx_stage, ctx + (size_t)e0 * A * 256, (size_t)ne * A * 256 * sizeof(float), cudaMemcpyDeviceToDevice, s));
         SNB_CUDA_TRY(cudaMemcpyAsync(h->xa, x_T + (size_t)e0 * N * 2, M * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
         float *result = (n_iter & 1) ? h->xb : h->xa;
         const int64_t key = ((int64_t)ne << 24) | ((int64_t)A << 8) | (int64_t)n_steps;
-        auto git = h->graphs.find(key);
+        auto git = fx ? h->graphs.end() : h->graphs.find(key);
         if (git != h->graphs.end()) {
             SNB_CUDA_TRY(cudaGraphLaunch(git->second, s));
             snb_count_launch(1 + n_iter * 26);   // kernels inside the replayed graph
-        } else if (h->use_graphs && s != nullptr && ++h->graph_uses[key] >= 2) {
+        } else if (!fx && h->use_graphs && s != nullptr && ++h->graph_uses[key] >= 2) {
             // second use of this shape: capture the sequence once, then replay it for every later chunk
             cudaGraph_t graph = nullptr;
             SNB_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
@@ -346,13 +457,15 @@ extern "C" int snb_jmid_eps(SnbJmid *h, const float *ctx, const float *x_t, floa
     SNB_REQUIRE(h && ctx && x_t && eps, SNB_EINVAL, "snb_jmid_eps: NULL argument");
     SNB_REQUIRE(t >= 1 && t <= 100, SNB_EINVAL, "snb_jmid_eps: t out of range");
     cudaStream_t s = (cudaStream_t)stream;
-    for (int e0 = 0; e0 < B; e0 += h->chunk_envs) {
-        const int ne = (B - e0) < h->chunk_envs ? (B - e0) : h->chunk_envs;
+    const bool fx = h->precision == SNB_PREC_FP32X;
+    const int ce = fx ? h->x_chunk_envs : h->chunk_envs;
+    for (int e0 = 0; e0 < B; e0 += ce) {
+        const int ne = (B - e0) < ce ? (B - e0) : ce;
         Plans *P = nullptr;
-        int rc = get_plans(h, ne, h->A, &P);
+        int rc = fx ? get_x_plans(h, ne, h->A, &P) : get_plans(h, ne, h->A, &P);
         if (rc) return rc;
         if ((rc = snb_k_hyper_ctx(h->hyper, ctx + (size_t)e0 * h->A * 256, h->gc, h->bc, ne * h->A, s))) return rc;
-        if ((rc = net_forward(h, P, x_t + (size_t)e0 * h->N * 2, nullptr, eps + (size_t)e0 * h->N * 2, t, t - 1, s))) return rc;
+        if ((rc = (fx ? net_forward_x : net_forward)(h, P, x_t + (size_t)e0 * h->N * 2, nullptr, eps + (size_t)e0 * h->N * 2, t, t - 1, s))) return rc;
     }
     return SNB_OK;
 }

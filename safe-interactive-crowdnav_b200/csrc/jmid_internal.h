@@ -68,5 +68,15 @@ int snb_k_tail_ddim(const bf16 *t4, const float *wl, const float *bl, const floa
                     float c_sqrt_1mab, float c_sqrt_ab, float c_sqrt_abn, float c_sqrt_1mabn, cudaStream_t s);
 int snb_k_integrate(const float *vel, const float *p0, float *pos, int B, int S, int A, int T, float dt, cudaStream_t s);
 
+// ---- fp32-class path (jmid_fp32x.cu) ----
+int snb_x_split3(const float *src, bf16 *dst, size_t rows, int K, int weight_order, int relu, cudaStream_t s);
+int snb_x_embed(const float *x, const float *w1, const float *b1, const float *gate, const float *hb, const float *pe, float *h,
+                int n_tok_total, int tok_per_env, int T, int A, cudaStream_t s);
+int snb_x_layernorm(const float *pre, const float *resid, const float *g, const float *b, float *out, int rows, cudaStream_t s);
+int snb_x_csl_apply(float *v, const float *gate, const float *hb, size_t rows, int N, int tok_per_env, int T, int A, cudaStream_t s);
+int snb_x_attention(const float *qkv, float *out, int n_seq, int seq_len, cudaStream_t s);
+int snb_x_tail_ddim(const float *t4, const float *wl, const float *bl, const float *gate, const float *hb, const float *x_t, float *x_next,
+                    float *eps_out, int n_tok_total, int tok_per_env, int T, int A, float c1, float c2, float c3, float c4, cudaStream_t s);
+
 #define HYPER_TOTAL 898 // 512 + 256 + 128 + 2 columns of the four hyper networks
 #define HYPER_LD 900    // row stride of the gate / bias tables (16-byte aligned rows)

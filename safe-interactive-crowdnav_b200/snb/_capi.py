@@ -125,6 +125,7 @@ _proto("snb_jmid_gemm_bf16", C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i3
 _proto("snb_jmid_attention", C.c_int, [_vp, _vp, _i32, _i32, _vp], required=False)
 _proto("snb_jmid_flops_per_iter", _d, [_i32, _i32, _i32, _i32], required=False)
 _proto("snb_jmid_denoise_agents", C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp], required=False)
+_proto("snb_jmid_set_precision", C.c_int, [_vp, _i32, _vp], required=False)
 _proto("snb_jmid_dims", C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)], required=False)
 _u64 = C.c_uint64
 _proto("snb_pred_create", C.c_int, [C.POINTER(_vp), C.POINTER(EncoderWeights), _vp, _i32, _i32, _vp], required=False)

@@ -69,7 +69,9 @@ def weights_struct(sd, device, T):
 
 
 class JmidDenoiser:
-    def __init__(self, state_dict, max_envs, A, S, T=8, joint=True, device="cuda"):
+    PRECISIONS = {"bf16": 0, "fp32x": 1}
+
+    def __init__(self, state_dict, max_envs, A, S, T=8, joint=True, device="cuda", precision="bf16"):
         if _capi.lib.snb_jmid_create is None:
             raise _capi.SnbError("libsnb.so was built without the denoiser")
         self.device = torch.device(device)
@@ -83,6 +85,18 @@ class JmidDenoiser:
                                                   int(self.joint), _capi.stream_ptr()), "snb_jmid_create")
             torch.cuda.current_stream().synchronize()
         del keep  # the library copied / converted everything it needs
+        self.precision = "bf16"
+        if precision != "bf16":
+            self.set_precision(precision)
+
+    def set_precision(self, precision):
+        """"bf16" (default: bf16 tensor-core operands, fp32 accumulation) or "fp32x" (fp32-class: split-bf16 GEMMs + fp32 SIMT attention,
+        the parity instrument against the reference's fp32 path; ~6x the FLOPs, 8 environments per chunk)."""
+        if precision not in self.PRECISIONS:
+            raise _capi.SnbError(f"unknown precision {precision!r} (bf16 | fp32x)")
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.snb_jmid_set_precision(self._h, self.PRECISIONS[precision], _capi.stream_ptr()), "snb_jmid_set_precision")
+        self.precision = precision
 
     def _chk(self, t, shape):
         assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == tuple(shape), (t.shape, shape)

@@ -97,7 +97,7 @@ class ForecasterBatch:
     """B environments x H humans.  `encoder` / `ddpm` as returned by load_checkpoint (or synthetic dicts of the same keys)."""
 
     def __init__(self, encoder, ddpm, max_envs, H, num_samples=20, num_ret=None, step_size=20, horizon=8, joint=True, dt=0.25,
-                 radius=3.0, device="cuda", seed=0):
+                 radius=3.0, device="cuda", seed=0, precision="bf16"):
         if _capi.lib.snb_pred_create is None:
             raise _capi.SnbError("libsnb.so was built without the predictor")
         self.device = torch.device(device)
@@ -106,7 +106,8 @@ class ForecasterBatch:
         self.B, self.H, self.S, self.T = int(max_envs), int(H), int(num_samples), int(horizon)
         self.k = self.S if num_ret is None else int(num_ret)
         self.step_size, self.joint, self.dt, self.radius, self.seed = int(step_size), bool(joint), float(dt), float(radius), int(seed)
-        self.denoiser = JmidDenoiser(ddpm, max_envs=self.B, A=self.H, S=self.S, T=self.T, joint=self.joint, device=device)
+        self.denoiser = JmidDenoiser(ddpm, max_envs=self.B, A=self.H, S=self.S, T=self.T, joint=self.joint, device=device,
+                                     precision=precision)
         w, keep = encoder_struct(encoder, self.device)
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
