@@ -193,6 +193,7 @@ struct CrowdParams {
     double *next_h;     // full_step == 2: [B, H, 4] next observable human states (px, py, vx, vy)
     double *next_robot; // full_step == 2: [B, n_actions, 2] constrained next robot position (optional)
     int thread_mode;    // phase 1: 0 = one warp per human (small launches), 1 = one thread per human (large batches)
+    int fast_lines;     // thread mode, plain ORCA: half-planes of every thread in shared memory (this many per thread), no local memory
 };
 
 struct Line { float px, py, dx, dy; };
@@ -786,7 +787,25 @@ __device__ void orca_predict_warp(const CrowdParams &P, const Tile &T, WarpScrat
 // the warp-cooperative path above, hence the same bits.  The warp path minimises the latency of one small launch (32 lanes
 // share one human); this path maximises throughput when there are enough humans to give every thread its own (ncu of the
 // warp path at 262 144 envs: 24 % of the warp slots occupied, issue slots 43 % busy, most lanes idle behind <= 10 neighbours).
-__device__ bool lp1_serial(const Line *lines, int lineNo, float radius, float optx, float opty, bool dirOpt, float &rx, float &ry)
+// Where a thread's ORCA lines live.  PtrLines: a per-thread array (local memory).  SmemLines: shared memory, interleaved so that
+// line l of thread t is the float4 at base[l * CROWD_THREADS] (base already offset by t): conflict-free 16-byte accesses, and none of
+// the local-memory traffic that the first thread-mode kernel spilled to L2 / DRAM (ncu r02: 1.8 GB written per 2^20-env step against
+// 0.65 GB of state).
+constexpr int CROWD_THREADS_C = 256;
+struct PtrLines {
+    const Line *p;
+    __device__ __forceinline__ Line operator[](int i) const { return p[i]; }
+};
+template <int STRIDE>
+struct SmemLinesT {
+    float4 *base;
+    __device__ __forceinline__ Line operator[](int i) const { const float4 v = base[i * STRIDE]; Line l; l.px = v.x; l.py = v.y; l.dx = v.z; l.dy = v.w; return l; }
+    __device__ __forceinline__ void set(int i, const Line &l) const { base[i * STRIDE] = make_float4(l.px, l.py, l.dx, l.dy); }
+};
+typedef SmemLinesT<CROWD_THREADS_C> SmemLines;
+
+template <class LA>
+__device__ bool lp1_serial(const LA &lines, int lineNo, float radius, float optx, float opty, bool dirOpt, float &rx, float &ry)
 {
     const Line li = lines[lineNo];
     const float dotProduct = dot2(li.px, li.py, li.dx, li.dy);
@@ -820,7 +839,8 @@ __device__ bool lp1_serial(const Line *lines, int lineNo, float radius, float op
     return true;
 }
 
-__device__ int lp2_serial(const Line *lines, int n, float radius, float optx, float opty, bool dirOpt, float &rx, float &ry)
+template <class LA>
+__device__ int lp2_serial(const LA &lines, int n, float radius, float optx, float opty, bool dirOpt, float &rx, float &ry)
 {
     if (dirOpt) { rx = optx * radius; ry = opty * radius; }
     else if (dot2(optx, opty, optx, opty) > radius * radius) {
@@ -829,7 +849,8 @@ __device__ int lp2_serial(const Line *lines, int n, float radius, float optx, fl
         rx = nx * radius; ry = ny * radius;
     } else { rx = optx; ry = opty; }
     for (int i = 0; i < n; ++i) {
-        if (det2(lines[i].dx, lines[i].dy, lines[i].px - rx, lines[i].py - ry) > 0.0f) {
+        const Line li = lines[i];
+        if (det2(li.dx, li.dy, li.px - rx, li.py - ry) > 0.0f) {
             const float tx = rx, ty = ry;
             if (!lp1_serial(lines, i, radius, optx, opty, dirOpt, rx, ry)) { rx = tx; ry = ty; return i; }
         }
@@ -837,7 +858,8 @@ __device__ int lp2_serial(const Line *lines, int n, float radius, float optx, fl
     return n;
 }
 
-__device__ void lp3_serial(const Line *lines, int n, int numObstLines, int beginLine, float radius, float &rx, float &ry, Line *proj)
+template <class LA>
+__device__ void lp3_serial(const LA &lines, int n, int numObstLines, int beginLine, float radius, float &rx, float &ry, Line *proj)
 {
     float distance = 0.0f;
     for (int i = beginLine; i < n; ++i) {
@@ -862,7 +884,7 @@ __device__ void lp3_serial(const Line *lines, int n, int numObstLines, int begin
                 proj[np++] = pl;
             }
             const float tx = rx, ty = ry;
-            if (lp2_serial(proj, np, radius, -li.dy, li.dx, true, rx, ry) < np) { rx = tx; ry = ty; }
+            if (lp2_serial(PtrLines{proj}, np, radius, -li.dy, li.dx, true, rx, ry) < np) { rx = tx; ry = ty; }
             distance = det2(li.dx, li.dy, li.px - rx, li.py - ry);
         }
     }
@@ -982,12 +1004,103 @@ __device__ void orca_predict_thread(const CrowdParams &P, const Tile &T, int e, 
     if (overflow && P.status) atomicExch(P.status, SNB_EOVERFLOW);
 
     float rx, ry;
-    const int lineFail = lp2_serial(lines, nLines, maxSpeed, prefx, prefy, false, rx, ry);
+    const int lineFail = lp2_serial(PtrLines{lines}, nLines, maxSpeed, prefx, prefy, false, rx, ry);
     if (lineFail < nLines) {
         Line proj[SNB_MAX_ORCA_LINES];
-        lp3_serial(lines, nLines, numObstLines, lineFail, maxSpeed, rx, ry, proj);
+        lp3_serial(PtrLines{lines}, nLines, numObstLines, lineFail, maxSpeed, rx, ry, proj);
     }
     out_vx = rx; out_vy = ry;
+}
+
+// The same program for the common shape -- plain ORCA (no obstacle lines), <= FAST_MAXO observed agents, <= FAST_LCAP neighbours --
+// with nothing in local memory: distances and ranks in registers (loops unrolled over FAST_MAXO), the half-planes in shared memory.
+// Same float operations in the same order as orca_predict_thread, hence the same bits; an exact distance tie that needs RVO2's
+// kd-tree visit order (simulators with > 10 agents) is handed to the general function.
+constexpr int FAST_MAXO = 12, FAST_LCAP = 12;
+// Returns -1 when the velocity is final, else lineFail: linearProgram2 stopped at that line and linearProgram3 still has to run on
+// (lines, n_nb, maxSpeed, the LP2 result in out_v).  The caller compacts those humans (~10 % of a crowd) onto the first threads of the
+// CTA before running LP3, so that a warp no longer pays LP3's long serial loops whenever ONE of its 32 lanes needs them.
+template <int STRIDE>
+__device__ int orca_predict_thread_fast(const CrowdParams &P, const Tile &T, float4 *s_lines, int e, int i, int genv, float &out_vx, float &out_vy,
+                                        int &out_n, float &out_speed)
+{
+    const SnbPolicyCfg &cfg = P.cfg;
+    const int H = P.st.H, E = P.st.E;
+    const int n_others = H - 1 + P.st.n_obs_extras;
+    const int k = e * H + i;
+    const double dpx = T.px[k], dpy = T.py[k];
+    const float px = (float)dpx, py = (float)dpy, vx = (float)T.vx[k], vy = (float)T.vy[k];
+    const float radius = (float)(T.rad[k] + 0.01 + cfg.safety_space);
+    const float maxSpeed = (float)T.vpref[k];
+    const float neighborDist = (float)cfg.neighbor_dist;
+    const float timeHorizon = (float)cfg.time_horizon;
+    const float timeStep = (float)cfg.time_step;
+    const int maxNeighbors = cfg.max_neighbors;
+
+    const double dvx = T.gx[k] - dpx, dvy = T.gy[k] - dpy;
+    const double speed = sqrt(fma(dvy, dvy, dvx * dvx));
+    double pvx, pvy;
+    if (cfg.policy == SNB_POLICY_ORCA_PLUS) {
+        const double vp = T.vpref[k] - 1e-3;
+        if (speed > vp) { pvx = dvx / speed * vp; pvy = dvy / speed * vp; } else { pvx = dvx; pvy = dvy; }
+    } else {
+        if (speed > 1) { pvx = dvx / speed; pvy = dvy / speed; } else { pvx = dvx; pvy = dvy; }
+    }
+    const float prefx = (float)pvx, prefy = (float)pvy;
+
+    float dsq[FAST_MAXO];
+    unsigned inmask = 0;
+#pragma unroll
+    for (int c = 0; c < FAST_MAXO; ++c) {
+        dsq[c] = INFINITY;
+        if (c < n_others) {
+            double a, b, cc, d, r;
+            int id;
+            load_other(T, H, E, e, i, c, a, b, cc, d, r, id);
+            const float ddx = px - (float)a, ddy = py - (float)b;
+            dsq[c] = dot2(ddx, ddy, ddx, ddy);
+            if (maxNeighbors > 0 && dsq[c] < neighborDist * neighborDist) inmask |= 1u << c;
+        }
+    }
+    bool tie = false;
+#pragma unroll
+    for (int c = 0; c < FAST_MAXO; ++c)
+#pragma unroll
+        for (int j = c + 1; j < FAST_MAXO; ++j)
+            tie = tie || ((((inmask >> c) & (inmask >> j)) & 1u) && dsq[j] == dsq[c]);
+    if (tie && n_others + 1 > 10) { orca_predict_thread(P, T, e, i, genv, out_vx, out_vy); return -1; }
+    const int n_in = __popc(inmask);
+    const int n_nb = n_in < maxNeighbors ? n_in : maxNeighbors;
+    int rk[FAST_MAXO];
+#pragma unroll
+    for (int c = 0; c < FAST_MAXO; ++c) {
+        int rank = 0;
+#pragma unroll
+        for (int j = 0; j < FAST_MAXO; ++j)
+            rank += (((inmask >> j) & 1u) && (dsq[j] < dsq[c] || (dsq[j] == dsq[c] && j < c))) ? 1 : 0;
+        rk[c] = ((inmask >> c) & 1u) ? rank : 0x7fffffff;
+    }
+    if (P.nbr_cnt) P.nbr_cnt[genv * H + i] = n_nb;
+
+    const SmemLinesT<STRIDE> lines{s_lines};
+    for (int r = 0; r < n_nb; ++r) {
+        int csel = 0;
+#pragma unroll
+        for (int c = 0; c < FAST_MAXO; ++c) csel = rk[c] == r ? c : csel;
+        double a, b, cc, d, rr;
+        int id;
+        load_other(T, H, E, e, i, csel, a, b, cc, d, rr, id);
+        lines.set(r, agent_orca_line(px, py, vx, vy, radius, (float)a, (float)b, (float)cc, (float)d,
+                                     (float)(rr + 0.01 + cfg.safety_space), 1.0f / timeHorizon, timeStep));
+        if (P.nbr) P.nbr[(size_t)(genv * H + i) * maxNeighbors + r] = id;
+    }
+    if (P.nbr) for (int r = n_nb; r < maxNeighbors; ++r) P.nbr[(size_t)(genv * H + i) * maxNeighbors + r] = -1;
+
+    float rx, ry;
+    const int lineFail = lp2_serial(lines, n_nb, maxSpeed, prefx, prefy, false, rx, ry);
+    out_vx = rx; out_vy = ry;
+    out_n = n_nb; out_speed = maxSpeed;
+    return lineFail < n_nb ? lineFail : -1;
 }
 
 // utils_plus.closest_point_on_segment (utils_plus.py:21-42)
@@ -1279,6 +1392,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 }
 
 #define CROWD_THREADS 256
+static_assert(CROWD_THREADS == CROWD_THREADS_C, "SmemLines stride");
 
 __global__ void __launch_bounds__(CROWD_THREADS, 3) crowd_step_kernel(const CrowdParams P)
 {
@@ -1302,7 +1416,11 @@ __global__ void __launch_bounds__(CROWD_THREADS, 3) crowd_step_kernel(const Crow
     T.segs = sd; sd += 4 * ((P.n_seg + 1) & ~1);
     double *s_next = sd; sd += 2 * EA;       // constrained human next positions
     uint64_t *bar = reinterpret_cast<uint64_t *>(sd); sd += 2;
-    WarpScratch *WS = reinterpret_cast<WarpScratch *>(sd);
+    WarpScratch *WS = reinterpret_cast<WarpScratch *>(sd);              // warp mode only
+    float4 *s_fast_lines = reinterpret_cast<float4 *>(sd);              // thread mode, fast path only (same bytes: the modes exclude each other)
+    int4 *s_lp3 = reinterpret_cast<int4 *>(s_fast_lines + (size_t)P.fast_lines * CROWD_THREADS);   // LP3 work queue, one entry per thread at most
+    int *s_lp3_count = reinterpret_cast<int *>(s_lp3 + CROWD_THREADS);
+    if (P.fast_lines && tid == 0) *s_lp3_count = 0;
 
     // ---- stage the tile: 8 human arrays by TMA bulk copy when 16-byte aligned, else by plain loads ----
     const int nA = nenv * H;
@@ -1351,11 +1469,32 @@ __global__ void __launch_bounds__(CROWD_THREADS, 3) crowd_step_kernel(const Crow
                 if (P.nbr_cnt) P.nbr_cnt[genv * H + i] = 0;
             } else {
                 float fx, fy;
-                orca_predict_thread(P, T, e, i, genv, fx, fy);
+                if (P.fast_lines) {
+                    int n_l; float spd;
+                    const int fail = orca_predict_thread_fast<CROWD_THREADS_C>(P, T, s_fast_lines + threadIdx.x, e, i, genv, fx, fy, n_l, spd);
+                    if (fail >= 0) {          // queue this human for the compacted LP3 pass below
+                        const int slot = atomicAdd(s_lp3_count, 1);
+                        s_lp3[slot] = make_int4(threadIdx.x | (task << 16), n_l | (fail << 8), __float_as_int(spd), 0);
+                    }
+                } else orca_predict_thread(P, T, e, i, genv, fx, fy);
                 ax = (double)fx; ay = (double)fy;
             }
             T.act[2 * task] = ax; T.act[2 * task + 1] = ay;
             if (!P.full_step && P.out_v) { P.out_v[2 * (goff + task)] = ax; P.out_v[2 * (goff + task) + 1] = ay; }
+        }
+        if (P.fast_lines) {
+            // ---- linearProgram3 for the humans whose LP2 failed, compacted onto the first threads of the CTA ----
+            __syncthreads();
+            const int n_q = *s_lp3_count;
+            for (int q = tid; q < n_q; q += blockDim.x) {
+                const int4 it = s_lp3[q];
+                const int owner = it.x & 0xffff, task = it.x >> 16, n_l = it.y & 0xff, fail = it.y >> 8;
+                float rx = (float)T.act[2 * task], ry = (float)T.act[2 * task + 1];     // the LP2 result (exactly representable: it was a float)
+                Line proj[FAST_LCAP];
+                lp3_serial(SmemLines{s_fast_lines + owner}, n_l, 0, fail, __int_as_float(it.z), rx, ry, proj);
+                T.act[2 * task] = (double)rx; T.act[2 * task + 1] = (double)ry;
+                if (!P.full_step && P.out_v) { P.out_v[2 * (goff + task)] = (double)rx; P.out_v[2 * (goff + task) + 1] = (double)ry; }
+            }
         }
     } else
     // ---- phase 1: one warp per human ----
@@ -1481,9 +1620,11 @@ __global__ void __launch_bounds__(CROWD_THREADS, 3) crowd_step_kernel(const Crow
         }
         P.st.px[g] = nx; P.st.py[g] = ny; P.st.vx[g] = c0; P.st.vy[g] = c1;
         P.st.theta[g] = atan2(c1, c0);
-        double ngx, ngy;
-        get_g_xy(P.door, nx, ny, P.st.fgx[g], P.st.fgy[g], ngx, ngy);
-        P.st.gx[g] = ngx; P.st.gy[g] = ngy;
+        if (P.door.enabled) {     // without a door Human.set_g_xy returns the final goal, which gx / gy already hold: nothing to write
+            double ngx, ngy;
+            get_g_xy(P.door, nx, ny, P.st.fgx[g], P.st.fgy[g], ngx, ngy);
+            P.st.gx[g] = ngx; P.st.gy[g] = ngy;
+        }
     }
     if (P.full_step == 2) return;
     __syncthreads(); // phase 2b's global_time stores are visible to the CTA after this barrier
@@ -1495,6 +1636,166 @@ __global__ void __launch_bounds__(CROWD_THREADS, 3) crowd_step_kernel(const Crow
         if (P.st.human_time[g] == 0 &&
             npnorm2(P.st.px[g] - P.st.gx[g], P.st.py[g] - P.st.gy[g]) < T.rad[task])
             P.st.human_time[g] = P.st.global_time[genv];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// crowd_orca_warp_kernel: the large-batch kernel of the simulator's common shape -- plain ORCA humans, no wall segments, one
+// robot -- with NO CTA-wide barrier: every warp owns floor(32 / H) whole environments (lane = human), keeps their state in its own
+// slice of shared memory and runs all phases of the step on it, synchronising with __syncwarp only.
+//
+// Why (ncu of the one-thread-per-human CTA kernel at 2^18 and 2^20 environments, profiles/r02_ncu_crowd_*): 39 % of the warp stall
+// samples sat on the __syncthreads between phase 1 and phase 2 -- seven warps waiting for the one whose lanes drew the longest
+// linear programs -- and issue slots were 40 % busy.  Here a warp that finishes early simply moves on to its own phase 2 and exits,
+// and a new CTA's warps take its place.  linearProgram3 (needed by ~10 % of the humans, but by ~95 % of the warps) is not run by the
+// lanes in lock-step: each human that needs it is handed to the whole warp (lp3_warp, lanes = half-planes, the shuffle-reduction LP
+// of the small-launch path).  Same float operations per human as everywhere else => bit-identical results.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int FW_WARPS = 4;
+static __host__ __device__ inline size_t fw_warp_bytes(int line_cap)
+{
+    return (size_t)(13 * 32 + 64) * sizeof(double) + (size_t)line_cap * 32 * sizeof(float4) + 32 * sizeof(Line);
+}
+
+__global__ void __launch_bounds__(32 * FW_WARPS) crowd_orca_warp_kernel(const CrowdParams P)
+{
+    extern __shared__ __align__(16) unsigned char fw_smem[];
+    const int H = P.st.H, E = P.st.E;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int epw = 32 / H;
+    const int env0 = (blockIdx.x * FW_WARPS + w) * epw;
+    const int nenv = min(epw, P.st.B - env0);
+    if (nenv <= 0) return;                                  // the whole warp leaves together; nobody waits for it
+    double *sd = reinterpret_cast<double *>(fw_smem + (size_t)w * fw_warp_bytes(P.fast_lines));
+    Tile T;
+    T.px = sd; sd += 32; T.py = sd; sd += 32; T.vx = sd; sd += 32; T.vy = sd; sd += 32;
+    T.rad = sd; sd += 32; T.gx = sd; sd += 32; T.gy = sd; sd += 32; T.vpref = sd; sd += 32;
+    T.ex_px = sd; sd += 32; T.ex_py = sd; sd += 32; T.ex_vx = sd; sd += 32; T.ex_vy = sd; sd += 32; T.ex_rad = sd; sd += 32;
+    T.act = nullptr; T.segs = nullptr;
+    double *s_next = sd; sd += 64;
+    float4 *s_lines = reinterpret_cast<float4 *>(sd);
+    Line *scratch = reinterpret_cast<Line *>(s_lines + (size_t)P.fast_lines * 32);
+
+    const int nA = nenv * H;
+    const bool live = lane < nA;
+    const int e = live ? lane / H : 0, i = lane - e * H;
+    const int genv = env0 + e;
+    const size_t g = (size_t)env0 * H + lane;
+    const bool on = live && !(P.active && !P.active[genv]);
+    if (live) {
+        T.px[lane] = P.st.px[g]; T.py[lane] = P.st.py[g]; T.vx[lane] = P.st.vx[g]; T.vy[lane] = P.st.vy[g];
+        T.rad[lane] = P.st.radius[g]; T.gx[lane] = P.st.gx[g]; T.gy[lane] = P.st.gy[g]; T.vpref[lane] = P.st.vpref[g];
+    }
+    if (lane < nenv * E) {
+        const size_t x = (size_t)env0 * E + lane;
+        T.ex_px[lane] = P.st.ex_px[x]; T.ex_py[lane] = P.st.ex_py[x]; T.ex_vx[lane] = P.st.ex_vx[x]; T.ex_vy[lane] = P.st.ex_vy[x];
+        T.ex_rad[lane] = P.st.ex_radius[x];
+    }
+    __syncwarp();
+
+    // ---- phase 1: ORCA per lane up to linearProgram2; linearProgram3 warp-cooperatively, one human at a time ----
+    float fx = 0.0f, fy = 0.0f, spd = 0.0f;
+    int fail = -1, n_l = 0;
+    if (on) fail = orca_predict_thread_fast<32>(P, T, s_lines + lane, e, i, genv, fx, fy, n_l, spd);
+    unsigned need = __ballot_sync(FULL, fail >= 0);
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int n = __shfl_sync(FULL, n_l, src), begin = __shfl_sync(FULL, fail, src);
+        const float r = __shfl_sync(FULL, spd, src);
+        float rx = __shfl_sync(FULL, fx, src), ry = __shfl_sync(FULL, fy, src);
+        Line my; my.px = 0.f; my.py = 0.f; my.dx = 1.f; my.dy = 0.f;
+        if (lane < n) my = SmemLinesT<32>{s_lines + src}[lane];
+        lp3_warp(my, n, 0, begin, r, rx, ry, lane, scratch);
+        if (lane == src) { fx = rx; fy = ry; }
+    }
+    const double c0 = (double)fx, c1 = (double)fy;
+    if (!P.full_step) {
+        if (on && P.out_v) { P.out_v[2 * g] = c0; P.out_v[2 * g + 1] = c1; }
+        return;
+    }
+
+    // ---- phase 2a: no wall segments -> the action is not clamped; next position (Agent.compute_position) ----
+    const double dt = P.cfg.time_step;
+    double nx = 0.0, ny = 0.0;
+    if (on) { nx = T.px[lane] + c0 * dt; ny = T.py[lane] + c1 * dt; s_next[2 * lane] = nx; s_next[2 * lane + 1] = ny; }
+    __syncwarp();
+
+    // ---- phase 2b: lane e < nenv is the robot of environment e (crowd_sim_plus.py:1058-1172, same expressions as crowd_step_kernel) ----
+    double gt_new = 0.0;
+    if (lane < nenv) {
+        const int re = lane, renv = env0 + re;
+        if (P.active && !P.active[renv]) {
+            if (P.reward) P.reward[renv] = 0.0;
+            if (P.flags) P.flags[renv] = 0;
+        } else {
+            const double rpx = T.ex_px[re * E], rpy = T.ex_py[re * E], rrad = T.ex_rad[re * E];
+            const double rtheta = P.st.rtheta[renv];
+            const double ra0 = P.robot_action[2 * (size_t)renv], ra1 = P.robot_action[2 * (size_t)renv + 1];
+            const int kin = P.st.robot_kinematics;
+            const double a0 = ra0, a1 = ra1;                      // no segments: constrain_agent_action_exact returns the action
+            double rnx, rny;
+            compute_position(rpx, rpy, rtheta, kin, a0, a1, dt, rnx, rny);
+            double dmin = INFINITY;
+            bool collision = false;
+            for (int h = 0; h < H; ++h) {
+                const int k = re * H + h;
+                const double closest = npnorm2(rnx - s_next[2 * k], rny - s_next[2 * k + 1]);
+                if (closest < (rrad + T.rad[k])) { collision = true; break; }
+                else if (closest < dmin) dmin = closest;
+            }
+            bool frozen;
+            if (kin == SNB_KIN_HOLONOMIC) frozen = sqrt(a0 * a0 + a1 * a1) * dt < 0.01;
+            else frozen = fabs(a0 * dt) < 0.01;
+            const double rgx = P.st.rgx[renv], rgy = P.st.rgy[renv];
+            const bool reached = npnorm2(rnx - rgx, rny - rgy) < rrad;
+            const double curr_dist = npnorm2(rgx - rnx, rgy - rny);
+            const double gt = P.st.global_time[renv];
+            double rew = 0.0;
+            int f = 0;
+            if (reached) { rew += P.rcfg.success_reward; f |= SNB_F_REACHED | SNB_F_DONE; }
+            else if (gt >= P.rcfg.time_limit) { rew += P.rcfg.timeout; f |= SNB_F_TIMEOUT | SNB_F_DONE; }
+            if (collision) { rew += P.rcfg.collision_penalty; f |= SNB_F_COLLISION; }
+            if (P.rcfg.discomfort && dmin < P.rcfg.discomfort_dist) {
+                rew += (dmin - P.rcfg.discomfort_dist) * P.rcfg.discomfort_penalty_factor * dt;
+                f |= SNB_F_DANGER;
+            }
+            if (P.rcfg.has_progress) {
+                rew += (P.st.prev_dist[renv] - curr_dist) * P.rcfg.progress_factor;
+                P.st.prev_dist[renv] = curr_dist;
+            }
+            if (frozen) { rew += P.rcfg.freezing_penalty; f |= SNB_F_FROZEN; }
+            if (P.reward) P.reward[renv] = rew;
+            if (P.dmin) P.dmin[renv] = dmin;
+            if (P.flags) P.flags[renv] = f;
+            const size_t gx = (size_t)renv * E;
+            P.st.ex_px[gx] = rnx; P.st.ex_py[gx] = rny;
+            if (kin == SNB_KIN_HOLONOMIC) {
+                P.st.ex_vx[gx] = a0; P.st.ex_vy[gx] = a1;
+                P.st.rtheta[renv] = atan2(a1, a0);
+            } else {
+                const double PI = 3.14159265358979323846;
+                const double un = py_mod(rtheta + a1, 2 * PI);
+                const double th = un > PI ? un - 2 * PI : un;
+                P.st.rtheta[renv] = th;
+                P.st.ex_vx[gx] = a0 * cos(th); P.st.ex_vy[gx] = a0 * sin(th);
+            }
+            gt_new = gt + dt;
+            P.st.global_time[renv] = gt_new;
+        }
+    }
+    gt_new = __shfl_sync(FULL, gt_new, e);                  // the clock of my environment after this step (human arrival times)
+
+    // ---- phase 2c: Human.step (integrate, heading, door goal) and arrival time; coalesced write-back straight from registers ----
+    if (on) {
+        P.st.px[g] = nx; P.st.py[g] = ny; P.st.vx[g] = c0; P.st.vy[g] = c1;
+        P.st.theta[g] = atan2(c1, c0);
+        double ggx = T.gx[lane], ggy = T.gy[lane];
+        if (P.door.enabled) {
+            get_g_xy(P.door, nx, ny, P.st.fgx[g], P.st.fgy[g], ggx, ggy);
+            P.st.gx[g] = ggx; P.st.gy[g] = ggy;
+        }
+        if (P.st.human_time[g] == 0 && npnorm2(nx - ggx, ny - ggy) < T.rad[lane]) P.st.human_time[g] = gt_new;
     }
 }
 
@@ -1515,12 +1816,13 @@ static int choose_epc(int H)
     return epc;
 }
 
-static size_t crowd_smem_bytes(int epc, int H, int E, int n_seg)
+static size_t crowd_smem_bytes(int epc, int H, int E, int n_seg, int fast_lines = 0)
 {
     const size_t EA = (size_t)((epc * H + 1) & ~1);
     const size_t EX = (size_t)((epc * (E > 0 ? E : 1) + 1) & ~1);
     size_t d = 8 * EA + 5 * EX + 2 * EA + 4 * (size_t)((n_seg + 1) & ~1) + 2 * EA + 2;
-    return d * sizeof(double) + sizeof(WarpScratch) * (CROWD_THREADS / 32) + 16;
+    const size_t scratch = fast_lines ? (size_t)(fast_lines + 1) * CROWD_THREADS * sizeof(float4) + 16 : sizeof(WarpScratch) * (CROWD_THREADS / 32);
+    return d * sizeof(double) + scratch + 16;
 }
 
 static int launch_crowd(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const SnbRewardCfg *rcfg, const SnbCrowdState *st,
@@ -1577,8 +1879,27 @@ static int launch_crowd(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const S
     }
     P.full_step = full_step;
     P.n_actions = n_actions; P.next_h = next_h; P.next_robot = next_robot;
+    if (P.thread_mode && P.n_vert == 0 && cfg->policy != SNB_POLICY_SFM && st->H - 1 + st->n_obs_extras <= FAST_MAXO &&
+        cfg->max_neighbors >= 1 && cfg->max_neighbors <= FAST_LCAP && !getenv("SNB_CROWD_NO_FAST") &&
+        crowd_smem_bytes(P.epc, st->H, st->E, P.n_seg, cfg->max_neighbors) <= 96 * 1024)
+        P.fast_lines = cfg->max_neighbors;
 
-    const size_t smem = crowd_smem_bytes(P.epc, st->H, st->E, P.n_seg);
+    // the barrier-free kernel: plain ORCA, no walls, the simulator's single robot, update / policy-only (not the what-if look-ahead)
+    if (P.fast_lines && P.n_seg == 0 && st->E == 1 && full_step != 2 && st->H <= 32 && !getenv("SNB_CROWD_NO_WARPOWN")) {
+        const int epw = 32 / st->H;
+        const size_t wsm = fw_warp_bytes(P.fast_lines) * FW_WARPS;
+        static std::once_flag once_w;
+        static cudaError_t attr_w = cudaSuccess;
+        std::call_once(once_w, [] { attr_w = cudaFuncSetAttribute(crowd_orca_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); });
+        SNB_CUDA_TRY(attr_w);
+        const int envs_per_cta = epw * FW_WARPS;
+        crowd_orca_warp_kernel<<<(st->B + envs_per_cta - 1) / envs_per_cta, 32 * FW_WARPS, wsm, (cudaStream_t)stream>>>(P);
+        snb_count_launch();
+        SNB_CUDA_TRY(cudaGetLastError());
+        return SNB_OK;
+    }
+
+    const size_t smem = crowd_smem_bytes(P.epc, st->H, st->E, P.n_seg, P.fast_lines);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] { attr_err = cudaFuncSetAttribute(crowd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); });

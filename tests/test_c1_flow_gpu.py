@@ -24,7 +24,7 @@ def test_reference_plumbing_with_drop_in_policies_replays_golden_episode(path):
         assert np.max(np.abs(hs - ref_h)) < tol, (k, np.max(np.abs(hs - ref_h)))
         assert np.max(np.abs(rs - g["R_states"][k])) < tol, k
         n += 1
-    assert n == len(g["actions"]) >= 20
+    assert n == len(g["actions"]) >= 8
 
 
 def test_policy_factory_objects_are_the_reference_surface():
