@@ -26,6 +26,7 @@ UNITS = [
     ("jmid_kernels.cu", []),
     ("jmid_gemm.cu", []),
     ("jmid_attn.cu", []),
+    ("jmid_attn2.cu", []),
     ("jmid_fp32x.cu", []),
     ("jmid_api.cu", []),
     ("pred_prep.cu", ["-fmad=false", "-Xcompiler", "-ffp-contract=off"]),

@@ -14,6 +14,15 @@ namespace {
 
 constexpr int D = 512, DFF = 1024, NL = 3;
 
+// SNB_ATTN_V2=1 selects the experimental second kernel (jmid_attn2.cu: 64-key blocks, P in TMEM) for A/B runs; measured on B200 it is
+// NOT faster (1005 vs 1038 TFLOP/s): its N = 64 S = Q K^T MMAs re-read the 4 KB Q slice from shared memory for half the math and run at
+// 48 clk instead of 32 (the 128 B / clk operand port), so the tensor side becomes the bound.  Default: jmid_attn.cu.
+bool attn_v1()
+{
+    static const bool v2 = [] { const char *e = getenv("SNB_ATTN_V2"); return e && e[0] == '1'; }();
+    return !v2;
+}
+
 struct LayerDev {
     bf16 *wqkv, *wo, *w1, *w2;
     float *bqkv, *bo, *b1, *b2, *n1w, *n1b, *n2w, *n2b;
@@ -23,6 +32,7 @@ struct Plans {
     int n_env = 0, M = 0, A = 0, N = 0; // A agents per env in this call (<= the handle's A), N = A*S*T tokens per env
     GemmPlan qkv[NL], out[NL], ff1[NL], ff2[NL], c3, c4;
     AttnPlan attn;
+    Attn2Plan attn2;
 };
 
 } // namespace
@@ -106,7 +116,8 @@ int get_plans(SnbJmid *h, int n_env, int A, Plans **out)
     }
     if (!rc) rc = snb_gemm_plan(&p.c3, h->h, h->wc3, h->t3, 0, p.M, 256, D);
     if (!rc) rc = snb_gemm_plan(&p.c4, h->t3, h->wc4, h->t4, 0, p.M, 128, 256);
-    if (!rc && h->joint) rc = snb_attn_plan(&p.attn, h->qkv, n_env, p.N);
+    if (!rc && h->joint) rc = snb_attn_plan(&p.attn, h->qkv, h->att, n_env, p.N);
+    if (!rc && h->joint) rc = snb_attn2_plan(&p.attn2, h->qkv, n_env, p.N);
     if (rc) return rc;
     h->plans[key] = p;
     *out = &h->plans[key];
@@ -126,7 +137,7 @@ int net_forward(SnbJmid *h, Plans *P, const float *x_in, float *x_next, float *e
         memset(&e, 0, sizeof(e));
         e.bias = h->L[l].bqkv;
         if ((rc = snb_gemm_launch(&P->qkv[l], EPI_BIAS_BF16, &e, h->num_sms, s))) return rc;
-        if (h->joint) rc = snb_attn_launch(&P->attn, h->att, s);
+        if (h->joint) rc = attn_v1() ? snb_attn_launch(&P->attn, s) : snb_attn2_launch(&P->attn2, h->att, s);
         else rc = snb_attn_small_launch(h->qkv, h->att, M / h->T, h->T, s);
         if (rc) return rc;
         e.bias = h->L[l].bo;
@@ -525,8 +536,14 @@ extern "C" int snb_jmid_gemm_bf16(const void *A, const void *W, const float *bia
 extern "C" int snb_jmid_attention(const void *qkv, void *out, int32_t n_env, int32_t n_tok, void *stream)
 {
     SNB_REQUIRE(qkv && out, SNB_EINVAL, "snb_jmid_attention: NULL argument");
-    AttnPlan p;
-    int rc = snb_attn_plan(&p, (const bf16 *)qkv, n_env, n_tok);
+    if (attn_v1()) {
+        AttnPlan p;
+        int rc = snb_attn_plan(&p, (const bf16 *)qkv, (bf16 *)out, n_env, n_tok);
+        if (rc) return rc;
+        return snb_attn_launch(&p, (cudaStream_t)stream);
+    }
+    Attn2Plan p;
+    int rc = snb_attn2_plan(&p, (const bf16 *)qkv, n_env, n_tok);
     if (rc) return rc;
-    return snb_attn_launch(&p, (bf16 *)out, (cudaStream_t)stream);
+    return snb_attn2_launch(&p, (bf16 *)out, (cudaStream_t)stream);
 }

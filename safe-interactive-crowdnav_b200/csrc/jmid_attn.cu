@@ -6,6 +6,7 @@
 // N x N score matrix in HBM.  Structure and measurements: see the comment above attn_fwd_kernel.
 #include <cfloat>
 #include <mutex>
+#include <type_traits>
 
 #include "jmid_internal.h"
 #include "tc_utils.cuh"
@@ -38,6 +39,13 @@ __device__ long long g_attn_trace[6 * 16 * 8];
 #define ATTN_TRACE(role, j, ev) do { } while (0)
 #endif
 
+__device__ __forceinline__ float fmax3(float a, float b, float c)   // FMNMX3: one instruction for two comparisons (sm_100)
+{
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
@@ -63,7 +71,7 @@ constexpr int ATTN_RING = 3;
 constexpr int ATTN_SMEM = TILE_BYTES * (2 + 2 + ATTN_RING) + 1024 + 256;
 
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmOut, const AttnArgs args)
 {
     constexpr int POLY_EVERY = SNB_ATTN_POLY_EVERY;   // one key pair in POLY_EVERY gets its 2^x from the FMA pipe (0 = none)
     extern __shared__ uint8_t smem_raw[];
@@ -264,7 +272,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
             if (t == 1 && !has_b) continue;
             float m_used = -INFINITY; // running max the exponents are taken against (raw score units)
             float l = 0.0f;
-            for (int j = 0; j < n_kv; ++j) {
+            // one 128-key block.  RAGGED is a compile-time flag: ptxas if-converts the masking of keys that do not exist into 128 ISETP +
+            // 128 SEL per row, a quarter of the loop's instructions -- only the copy that runs the item's LAST block carries them.
+            auto block = [&](int j, auto ragged_tag) {
+                constexpr bool RAGGED = decltype(ragged_tag)::value;
                 const uint32_t ph = (g + j) & 1;
                 ATTN_TRACE(t, j, 0);
                 tc::mbar_wait(&s_full[t], ph);
@@ -281,8 +292,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
                 tc::tc_fence_before();
                 tc::mbar_arrive(&s_free[t]);  // S_t may be overwritten by the next block's Q K^T
                 ATTN_TRACE(t, j, 2);
-                const int valid = n_tok - j * BKV; // keys of this block that exist
-                if (valid < BKV) {                 // ragged last block: keys that do not exist score -inf
+                if constexpr (RAGGED) {            // ragged last block: keys that do not exist score -inf
+                    const int valid = n_tok - j * BKV; // keys of this block that exist
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         if (i >= valid) s0[i] = 0xff800000u;
@@ -291,13 +302,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
                         if (96 + i >= valid) s3[i] = 0xff800000u;
                     }
                 }
-                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+                float mx0 = __uint_as_float(s0[0]), mx1 = __uint_as_float(s1[0]), mx2 = __uint_as_float(s2[0]), mx3 = __uint_as_float(s3[0]);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    mx0 = fmaxf(mx0, __uint_as_float(s0[i])); mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
-                    mx2 = fmaxf(mx2, __uint_as_float(s2[i])); mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
+                for (int i = 1; i < 31; i += 2) {
+                    mx0 = fmax3(mx0, __uint_as_float(s0[i]), __uint_as_float(s0[i + 1])); mx1 = fmax3(mx1, __uint_as_float(s1[i]), __uint_as_float(s1[i + 1]));
+                    mx2 = fmax3(mx2, __uint_as_float(s2[i]), __uint_as_float(s2[i + 1])); mx3 = fmax3(mx3, __uint_as_float(s3[i]), __uint_as_float(s3[i + 1]));
                 }
-                const float bmax = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                const float bmax = fmax3(fmax3(mx0, mx1, __uint_as_float(s0[31])), fmax3(mx2, mx3, __uint_as_float(s1[31])),
+                                         fmaxf(__uint_as_float(s2[31]), __uint_as_float(s3[31])));
                 if (j == 0) {
                     m_used = bmax;
                 } else if (__any_sync(0xffffffffu, (bmax - m_used) * c > RESCALE_THRESHOLD)) {
@@ -345,57 +357,77 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs args)
                         s[i] = tc::pack_bf16(el, eh);
                     }
                 };
-                exp_pack(s0); exp_pack(s1); exp_pack(s2); exp_pack(s3);
-                {
-                    float a0, a1, b0, b1;
-                    tc::f2_unpack(sumA, a0, a1);
-                    tc::f2_unpack(sumB, b0, b1);
-                    l += (a0 + a1) + (b0 + b1);
-                }
-                ATTN_TRACE(t, j, 3);
-                // ... then the P row goes to shared memory once PV_t(j-1) has consumed the previous one (normally long ago)
-                if (g + j > 0) tc::mbar_wait(&pv_done[t], ph ^ 1);   // (for j == 0: the previous item's last PV, already awaited by its epilogue)
                 auto store = [&](const uint32_t (&s)[32], int box, int chunk0) {   // 32 keys = four 16-byte chunks of my P row
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         *reinterpret_cast<uint4 *>(p_row + box * (TILE_BYTES / 2) + (((chunk0 + q) ^ sw) << 4)) =
                             make_uint4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
                 };
-                store(s0, 0, 0); store(s1, 0, 4); store(s2, 1, 0); store(s3, 1, 4);
+                // Each 32-key quarter of the P row goes to shared memory as soon as its exponentials exist, so the LSU drains the
+                // 32 KB tile (>= 256 clk of store bandwidth per tile) underneath the MUFU / FMA work of the next quarter instead of
+                // after all of it (the trace of the exps-then-stores order: 471 clk of the block's 2930 on the stores alone).
+                // PV_t(j-1) must have consumed the previous P first -- it was issued a whole softmax ago.
+                exp_pack(s0);
+                if (g + j > 0) tc::mbar_wait(&pv_done[t], ph ^ 1);   // (for j == 0: the previous item's last PV, already awaited by its epilogue)
+                if (j == 0 && g > 0) {
+                    // the previous item's O tile was staged in this P tile: its TMA store must have finished READING it
+                    if (row_in_tile == 0) tc::tma_store_wait_read<0>();
+                    tc::named_bar_sync(1 + t, 128);
+                }
+                store(s0, 0, 0);
+                exp_pack(s1); store(s1, 0, 4);
+                exp_pack(s2); store(s2, 1, 0);
+                exp_pack(s3);
+                ATTN_TRACE(t, j, 3);
+                store(s3, 1, 4);
+                {
+                    float a0, a1, b0, b1;
+                    tc::f2_unpack(sumA, a0, a1);
+                    tc::f2_unpack(sumB, b0, b1);
+                    l += (a0 + a1) + (b0 + b1);
+                }
                 ATTN_TRACE(t, j, 4);
                 tc::fence_proxy_async();      // generic-proxy stores -> visible to the tensor core's async-proxy reads
                 tc::mbar_arrive(&p_ready[t]);
                 ATTN_TRACE(t, j, 5);
-            }
+            };
+            for (int j = 0; j < n_kv - 1; ++j) block(j, std::false_type{});
+            if (n_tok % BKV) block(n_kv - 1, std::true_type{}); else block(n_kv - 1, std::false_type{});
             // final: O / l -> global
             tc::mbar_wait(&pv_done[t], (g + n_kv - 1) & 1);
             __syncwarp();
             tc::tc_fence_after();
             const float inv_l = 1.0f / l;
-            const int row = q0 + t * BQ + row_in_tile;
-            bf16 *dst = args.out + ((size_t)env * n_tok + row) * (NHEAD * HD) + head * HD;
+            // O / l goes out through the (now idle) P tile and ONE TMA store per 64-column box instead of per-thread 16-byte stores
+            // to 32 different rows per instruction (trace of that version: 5 700 clk of the item's 46 000 in this epilogue).  Rows
+            // beyond the sequence are clipped by the tensor map.
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 uint32_t r[32];
                 tc::tmem_ld_32x32(o_addr + ch * 32, r);
                 tc::tmem_ld_wait();
-                if (row < n_tok) {
-                    uint4 *o4 = reinterpret_cast<uint4 *>(dst + ch * 32);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint4 o;
-                        o.x = tc::pack_bf16(__uint_as_float(r[8 * q + 0]) * inv_l, __uint_as_float(r[8 * q + 1]) * inv_l);
-                        o.y = tc::pack_bf16(__uint_as_float(r[8 * q + 2]) * inv_l, __uint_as_float(r[8 * q + 3]) * inv_l);
-                        o.z = tc::pack_bf16(__uint_as_float(r[8 * q + 4]) * inv_l, __uint_as_float(r[8 * q + 5]) * inv_l);
-                        o.w = tc::pack_bf16(__uint_as_float(r[8 * q + 6]) * inv_l, __uint_as_float(r[8 * q + 7]) * inv_l);
-                        o4[q] = o;
-                    }
+                for (int q = 0; q < 4; ++q) {
+                    uint4 o;
+                    o.x = tc::pack_bf16(__uint_as_float(r[8 * q + 0]) * inv_l, __uint_as_float(r[8 * q + 1]) * inv_l);
+                    o.y = tc::pack_bf16(__uint_as_float(r[8 * q + 2]) * inv_l, __uint_as_float(r[8 * q + 3]) * inv_l);
+                    o.z = tc::pack_bf16(__uint_as_float(r[8 * q + 4]) * inv_l, __uint_as_float(r[8 * q + 5]) * inv_l);
+                    o.w = tc::pack_bf16(__uint_as_float(r[8 * q + 6]) * inv_l, __uint_as_float(r[8 * q + 7]) * inv_l);
+                    *reinterpret_cast<uint4 *>(p_row + (ch >> 1) * (TILE_BYTES / 2) + ((((ch & 1) * 4 + q) ^ sw) << 4)) = o;
                 }
             }
             tc::tc_fence_before();
             tc::mbar_arrive(&o_free[t]);      // O_t may be overwritten by the next item's first PV
+            tc::fence_proxy_async();
+            tc::named_bar_sync(1 + t, 128);   // the four warps of this tile: the whole O tile is in shared memory
+            if (row_in_tile == 0) {
+                tc::tma_store_3d(&tmOut, sP + t * TILE_BYTES, head * HD, q0 + t * BQ, env);
+                tc::tma_store_3d(&tmOut, sP + t * TILE_BYTES + TILE_BYTES / 2, head * HD + 64, q0 + t * BQ, env);
+                tc::tma_store_commit();
+            }
             g += n_kv;
         }
+        if (row_in_tile == 0) tc::tma_store_wait<0>();    // the last O tile has left shared memory before the CTA exits
     }
     __syncthreads();
 #ifdef SNB_ATTN_TRACE
@@ -451,21 +483,23 @@ __global__ void attn_small_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict
 
 } // namespace
 
-int snb_attn_plan(AttnPlan *plan, const bf16 *qkv, int n_env, int n_tok)
+int snb_attn_plan(AttnPlan *plan, const bf16 *qkv, bf16 *out, int n_env, int n_tok)
 {
     SNB_REQUIRE(n_env > 0 && n_tok > 0, SNB_EINVAL, "attention: bad sizes");
-    plan->n_env = n_env; plan->n_tok = n_tok;
-    return snb_make_tmap_3d(&plan->tmQKV, qkv, (uint64_t)n_env, (uint64_t)n_tok, 1536, BKV);
+    plan->n_env = n_env; plan->n_tok = n_tok; plan->out = out;
+    int rc = snb_make_tmap_3d(&plan->tmQKV, qkv, (uint64_t)n_env, (uint64_t)n_tok, 1536, BKV);
+    if (rc) return rc;
+    return snb_make_tmap_3d(&plan->tmOut, out, (uint64_t)n_env, (uint64_t)n_tok, 512, BQ);   // O tiles: 128 rows x 64 columns per store
 }
 
-int snb_attn_launch(const AttnPlan *plan, bf16 *out, cudaStream_t stream)
+int snb_attn_launch(const AttnPlan *plan, cudaStream_t stream)
 {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM); });
     SNB_CUDA_TRY(attr_err);
     AttnArgs a;
-    a.out = out; a.n_tok = plan->n_tok;
+    a.out = plan->out; a.n_tok = plan->n_tok;
     a.scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
     a.n_qp = (plan->n_tok + 2 * BQ - 1) / (2 * BQ);
     a.n_items = a.n_qp * NHEAD * plan->n_env;
@@ -476,7 +510,7 @@ int snb_attn_launch(const AttnPlan *plan, bf16 *out, cudaStream_t stream)
         SNB_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const int grid = a.n_items < num_sms ? a.n_items : num_sms;   // persistent: one CTA per SM walks the item list
-    attn_fwd_kernel<<<grid, ATTN_THREADS, ATTN_SMEM, stream>>>(plan->tmQKV, a);
+    attn_fwd_kernel<<<grid, ATTN_THREADS, ATTN_SMEM, stream>>>(plan->tmQKV, plan->tmOut, a);
     snb_count_launch();
     SNB_CUDA_TRY(cudaGetLastError());
     return SNB_OK;

@@ -42,11 +42,19 @@ int snb_gemm_launch(const GemmPlan *plan, int epi_kind, const GemmEpi *epi, int 
 // qkv [n_env, n_tok, 1536] bf16 (Q | K | V, 4 heads x 128 each) -> out [n_env * n_tok, 512] bf16; one unmasked
 // sequence of n_tok tokens per environment.
 struct AttnPlan {
-    CUtensorMap tmQKV;
+    CUtensorMap tmQKV, tmOut;   // out [n_env, n_tok, 512]: the O tiles leave through TMA stores (rows beyond the sequence are clipped)
+    bf16 *out;
     int n_env, n_tok;
 };
-int snb_attn_plan(AttnPlan *plan, const bf16 *qkv, int n_env, int n_tok);
-int snb_attn_launch(const AttnPlan *plan, bf16 *out, cudaStream_t stream);
+int snb_attn_plan(AttnPlan *plan, const bf16 *qkv, bf16 *out, int n_env, int n_tok);
+int snb_attn_launch(const AttnPlan *plan, cudaStream_t stream);
+// second-generation kernel (jmid_attn2.cu): 64-key blocks, P in TMEM, ten-slot K / V ring
+struct Attn2Plan {
+    CUtensorMap tmQ, tmKV;   // boxes of 128 (queries) and 64 (keys) rows x 64 columns
+    int n_env, n_tok;
+};
+int snb_attn2_plan(Attn2Plan *plan, const bf16 *qkv, int n_env, int n_tok);
+int snb_attn2_launch(const Attn2Plan *plan, bf16 *out, cudaStream_t stream);
 // iMID: independent sequences of T (<= 32) tokens; qkv [n_seq * T, 1536] -> out [n_seq * T, 512]
 int snb_attn_small_launch(const bf16 *qkv, bf16 *out, int n_seq, int T, cudaStream_t stream);
 
