@@ -274,6 +274,8 @@ def run_ours(args):
     pk = peaks()
     roof, roof_other = kernel_rooflines(den, ktimes, pk, B, NS, ms / args.steps)
     sim_only = sim_only_lines(dev, pk, ENV_CFG) if (rank == 0 and not args.skip_sim_only) else None
+    plugin_b1 = plugin_b1_latency() if (rank == 0 and not args.skip_sim_only) else None
+    precision = precision_lines(dev, ddpm_w, A, S, T, NS) if (rank == 0 and not args.skip_sim_only) else None
 
     # ---- end-of-episode metric gather (the only collective of the path) ----
     if dist is not None:
@@ -307,6 +309,8 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roof, "roofline_other": roof_other,
             "sim_only": sim_only,
+            "plugin_b1": plugin_b1,
+            "precision_modes": precision,
             "cpu_baseline": cpu,
             "bound_note": "at sustained bf16 peak the reference semantics (S=20 cross-sample attention) bound sim+JMID at "
                           f"{pk['tf_sustained'] * 1e12 / (den.flops_per_iter() * NS):.0f} env-steps/s per GPU (BASELINE.md section 3)",
@@ -439,6 +443,62 @@ def run_denoise_only(args):
                                     f"{fl / 1e9:.1f} GFLOP (BASELINE.md section 3)"}})
     if dist is not None:
         dist.destroy_process_group()
+
+
+def plugin_b1_latency():
+    """The path the reference itself would call: one `policy.predict(JointState)` per human per step through the drop-in policy
+    objects (B = 1: H2D of the joint state, one launch, D2H of the action, synchronise).  Microseconds per call, next to the
+    reference's own ~290 us SFM call (its ORCA call could not be run: rvo2 is absent)."""
+    from snb.policy.policy_factory import policy_factory
+    from snb.utils.state_plus import FullState, JointState, ObservableState
+    rng = np.random.default_rng(0)
+    out = {}
+    for name, n_others, segs in (("orca", 10, []), ("orca_plus", 10, [[(-0.875, -4.0), (-0.875, 4.0)], [(0.875, -4.0), (0.875, 4.0)]]),
+                                 ("sfm", 25, [[(-3.0, -12.0), (-3.0, 12.0)], [(3.0, -12.0), (3.0, 12.0)]])):
+        pol = policy_factory[name]()
+        pol.time_step = 0.25
+        if name == "sfm":
+            for k, v in dict(radius=0.2, A=3.0, B=0.18, KI=1.0, A_static=2.0, B_static=0.025, A_bottleneck=6.0, B_bottleneck=0.12).items():
+                setattr(pol, k, v)
+        me = FullState(0.0, 0.0, 0.3, 0.1, 0.3, 3.0, 2.0, 1.0, 0.0)
+        others = [ObservableState(*rng.uniform(-0.8 if segs else -3, 0.8 if segs else 3, 2), *rng.uniform(-1, 1, 2), 0.3) for _ in range(n_others)]
+        st = JointState(me, others, segs)
+        for _ in range(20):
+            pol.predict(st)
+        t0 = time.perf_counter()
+        n = 300
+        for _ in range(n):
+            pol.predict(st)
+        out[name] = {"us_per_predict": (time.perf_counter() - t0) / n * 1e6, "others": n_others, "segments": len(segs)}
+    out["note"] = "snb.policy.<X>().predict(JointState) -> ActionXY, wall clock incl. the ctypes packing; reference SFM.predict: ~290 us (1 core)"
+    return out
+
+
+def precision_lines(dev, ddpm_w, A, S, T, NS):
+    """The same 20-step denoise in both arithmetic modes at a small batch (8 envs): bf16 (the product path) and fp32x (split-bf16
+    GEMMs + fp32 attention, the parity instrument whose eps error vs the reference's fp32 is 5.7e-5).  env-predictions/s each."""
+    from snb.jmid import JmidDenoiser
+    B = 8
+    g = torch.Generator(device=dev).manual_seed(7)
+    ctx = torch.randn(B, A, 256, device=dev, generator=g) * 0.3
+    xT = torch.randn(B, S * A, T, 2, device=dev, generator=g)
+    out = {}
+    den = JmidDenoiser(ddpm_w, max_envs=B, A=A, S=S, T=T, joint=True, device=dev)
+    for mode in ("bf16", "fp32x"):
+        den.set_precision(mode)
+        for _ in range(2):
+            v = den.denoise(ctx, xT, n_steps=NS)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); v = den.denoise(ctx, xT, n_steps=NS); b.record(); torch.cuda.synchronize()
+        out[mode] = {"env_predictions_per_s": B / (a.elapsed_time(b) * 1e-3), "ms": a.elapsed_time(b), "envs": B}
+        out[mode + "_v"] = v
+    d = (out.pop("bf16_v") - out.pop("fp32x_v")).abs().max().item()
+    out["max_abs_velocity_difference_bf16_vs_fp32x"] = d
+    out["note"] = "fp32x is ~6x the tensor FLOPs (3-way bf16 split) + SIMT fp32 attention: a parity instrument, not a product path"
+    del den
+    torch.cuda.empty_cache()
+    return out
 
 
 def sim_only_lines(dev, pk, cfg_text):
