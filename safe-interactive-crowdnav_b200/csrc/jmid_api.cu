@@ -26,11 +26,15 @@ bool attn_v1()
 struct LayerDev {
     bf16 *wqkv, *wo, *w1, *w2;
     float *bqkv, *bo, *b1, *b2, *n1w, *n1b, *n2w, *n2b;
+    // LayerNorm fold: linear1 with norm1 of this layer folded in; in_proj with norm2 of the PREVIOUS layer (layers 1, 2)
+    bf16 *w1_f, *wqkv_f;
+    float *cs_1, *b1_f, *cs_qkv, *bqkv_f;
 };
 
 struct Plans {
     int n_env = 0, M = 0, A = 0, N = 0; // A agents per env in this call (<= the handle's A), N = A*S*T tokens per env
     GemmPlan qkv[NL], out[NL], ff1[NL], ff2[NL], c3, c4;
+    GemmPlan qkv_f[NL], ff1_f[NL], ff2_f[NL], c3_f;   // LayerNorm-fold dataflow: z1 lives in `pre`, z2 in `y`
     AttnPlan attn;
     Attn2Plan attn2;
 };
@@ -42,7 +46,10 @@ struct SnbJmid {
     std::vector<void *> allocs;
     // weights
     LayerDev L[NL];
-    bf16 *wc3, *wc4;
+    bf16 *wc3, *wc4, *wc3_f = nullptr;
+    float *cs_c3 = nullptr, *bc3_f = nullptr;
+    float2 *stats1 = nullptr, *stats2 = nullptr;   // [M,4] (sum, sum of squares) per 128-column slice of z1 / z2
+    int ln_fold = 1;
     float *c1_w, *c1_b, *c3_b, *c4_b, *lin_w, *lin_b, *pe;
     HyperW hyper[4];
     float betas[101], alpha_bars[101];
@@ -114,6 +121,14 @@ int get_plans(SnbJmid *h, int n_env, int A, Plans **out)
         if (!rc) rc = snb_gemm_plan(&p.ff1[l], h->y, h->L[l].w1, h->ff, 0, p.M, DFF, D);
         if (!rc) rc = snb_gemm_plan(&p.ff2[l], h->ff, h->L[l].w2, h->pre, 0, p.M, D, DFF);
     }
+    if (h->ln_fold) {
+        for (int l = 0; l < NL && !rc; ++l) {
+            if (l > 0) rc = snb_gemm_plan(&p.qkv_f[l], h->y, h->L[l].wqkv_f, h->qkv, 0, p.M, 3 * D, D);
+            if (!rc) rc = snb_gemm_plan(&p.ff1_f[l], h->pre, h->L[l].w1_f, h->ff, 0, p.M, DFF, D);
+            if (!rc) rc = snb_gemm_plan(&p.ff2_f[l], h->ff, h->L[l].w2, h->y, 0, p.M, D, DFF);
+        }
+        if (!rc) rc = snb_gemm_plan(&p.c3_f, h->y, h->wc3_f, h->t3, 0, p.M, 256, D);
+    }
     if (!rc) rc = snb_gemm_plan(&p.c3, h->h, h->wc3, h->t3, 0, p.M, 256, D);
     if (!rc) rc = snb_gemm_plan(&p.c4, h->t3, h->wc4, h->t4, 0, p.M, 128, 256);
     if (!rc && h->joint) rc = snb_attn_plan(&p.attn, h->qkv, h->att, n_env, p.N);
@@ -133,6 +148,38 @@ int net_forward(SnbJmid *h, Plans *P, const float *x_in, float *x_next, float *e
     rc = snb_k_embed(x_in, h->c1_w, h->c1_b, h->gate, h->hb, h->pe, h->h, M, P->N, h->T, P->A, s);
     if (rc) return rc;
     GemmEpi e;
+    if (h->ln_fold) {
+        // LayerNorm folded into the GEMMs (jmid_gemm.cu): z1 = h + attn -> `pre` (+ stats1), z2 = LN1(z1) + ff -> `y` (+ stats2); no
+        // LayerNorm kernel, no normalised activation is ever written to HBM.
+        for (int l = 0; l < NL; ++l) {
+            memset(&e, 0, sizeof(e));
+            if (l == 0) { e.bias = h->L[0].bqkv; rc = snb_gemm_launch(&P->qkv[0], EPI_BIAS_BF16, &e, h->num_sms, s); }
+            else {
+                e.bias = h->L[l].bqkv_f; e.fold = 1; e.colsum = h->L[l].cs_qkv; e.stats_in = h->stats2;
+                rc = snb_gemm_launch(&P->qkv_f[l], EPI_BIAS_BF16, &e, h->num_sms, s);
+            }
+            if (rc) return rc;
+            if (h->joint) rc = attn_v1() ? snb_attn_launch(&P->attn, s) : snb_attn2_launch(&P->attn2, h->att, s);
+            else rc = snb_attn_small_launch(h->qkv, h->att, M / h->T, h->T, s);
+            if (rc) return rc;
+            memset(&e, 0, sizeof(e));                       // out-proj: z1 = attn W_o^T + b_o + (layer input)
+            e.bias = h->L[l].bo; e.stats_out = h->stats1;
+            if (l == 0) { e.res = 1; e.resid = h->h; }
+            else { e.res = 2; e.resid = h->y; e.res_stats = h->stats2; e.res_gamma = h->L[l - 1].n2w; e.res_beta = h->L[l - 1].n2b; }
+            if ((rc = snb_gemm_launch(&P->out[l], EPI_BIAS_BF16, &e, h->num_sms, s))) return rc;
+            memset(&e, 0, sizeof(e));                       // linear1 on LN1(z1), folded
+            e.bias = h->L[l].b1_f; e.fold = 1; e.colsum = h->L[l].cs_1; e.stats_in = h->stats1;
+            if ((rc = snb_gemm_launch(&P->ff1_f[l], EPI_BIAS_RELU_BF16, &e, h->num_sms, s))) return rc;
+            memset(&e, 0, sizeof(e));                       // linear2: z2 = ff W_2^T + b_2 + LN1(z1)
+            e.bias = h->L[l].b2; e.res = 2; e.resid = h->pre; e.res_stats = h->stats1; e.res_gamma = h->L[l].n1w; e.res_beta = h->L[l].n1b;
+            e.stats_out = h->stats2;
+            if ((rc = snb_gemm_launch(&P->ff2_f[l], EPI_BIAS_BF16, &e, h->num_sms, s))) return rc;
+        }
+        memset(&e, 0, sizeof(e));                           // concat3 on LN2(z2) of the last layer, folded
+        e.bias = h->bc3_f; e.fold = 1; e.colsum = h->cs_c3; e.stats_in = h->stats2;
+        e.gate = h->gate + 512; e.hbias = h->hb + 512; e.tab_ld = HYPER_LD; e.tok_per_env = P->N; e.T = h->T; e.A = P->A;
+        if ((rc = snb_gemm_launch(&P->c3_f, EPI_CSL_BF16, &e, h->num_sms, s))) return rc;
+    } else {
     for (int l = 0; l < NL; ++l) {
         memset(&e, 0, sizeof(e));
         e.bias = h->L[l].bqkv;
@@ -153,6 +200,9 @@ int net_forward(SnbJmid *h, Plans *P, const float *x_in, float *x_next, float *e
     e.bias = h->c3_b; e.gate = h->gate + 512; e.hbias = h->hb + 512; e.tab_ld = HYPER_LD;
     e.tok_per_env = P->N; e.T = h->T; e.A = P->A;
     if ((rc = snb_gemm_launch(&P->c3, EPI_CSL_BF16, &e, h->num_sms, s))) return rc;
+    }
+    memset(&e, 0, sizeof(e));
+    e.tab_ld = HYPER_LD; e.tok_per_env = P->N; e.T = h->T; e.A = P->A;
     e.bias = h->c4_b; e.gate = h->gate + 768; e.hbias = h->hb + 768;
     if ((rc = snb_gemm_launch(&P->c4, EPI_CSL_BF16, &e, h->num_sms, s))) return rc;
     // DDIM coefficients in fp32 like torch: (1 - ab).sqrt(), ab.sqrt(), ab_next.sqrt(), (1 - ab_next).sqrt()
@@ -326,8 +376,31 @@ extern "C" int snb_jmid_create(SnbJmid **out, const SnbJmidWeights *w, int32_t m
         TRY(dup_f32(h, &h->L[l].n2w, (const float *)lw.norm2_w, D, s));
         TRY(dup_f32(h, &h->L[l].n2b, (const float *)lw.norm2_b, D, s));
     }
+    {
+        const char *fe = getenv("SNB_LN_FOLD");
+        h->ln_fold = fe ? atoi(fe) : 1;
+    }
+    if (h->ln_fold) {
+        for (int l = 0; l < NL; ++l) {
+            const SnbEncLayerWeights &lw = w->layers[l];
+            TRY(dev_alloc(h, &h->L[l].w1_f, (size_t)DFF * D)); TRY(dev_alloc(h, &h->L[l].cs_1, DFF)); TRY(dev_alloc(h, &h->L[l].b1_f, DFF));
+            TRY(snb_k_fold_ln((const float *)lw.lin1_w, (const float *)lw.norm1_w, (const float *)lw.norm1_b, (const float *)lw.lin1_b,
+                              h->L[l].w1_f, h->L[l].cs_1, h->L[l].b1_f, DFF, D, s));
+            if (l > 0) {
+                const SnbEncLayerWeights &pw = w->layers[l - 1];
+                TRY(dev_alloc(h, &h->L[l].wqkv_f, (size_t)3 * D * D)); TRY(dev_alloc(h, &h->L[l].cs_qkv, 3 * D)); TRY(dev_alloc(h, &h->L[l].bqkv_f, 3 * D));
+                TRY(snb_k_fold_ln((const float *)lw.in_proj_w, (const float *)pw.norm2_w, (const float *)pw.norm2_b, (const float *)lw.in_proj_b,
+                                  h->L[l].wqkv_f, h->L[l].cs_qkv, h->L[l].bqkv_f, 3 * D, D, s));
+            }
+        }
+        const SnbEncLayerWeights &last = w->layers[NL - 1];
+        TRY(dev_alloc(h, &h->wc3_f, (size_t)256 * D)); TRY(dev_alloc(h, &h->cs_c3, 256)); TRY(dev_alloc(h, &h->bc3_f, 256));
+        TRY(snb_k_fold_ln((const float *)w->concat3.layer_w, (const float *)last.norm2_w, (const float *)last.norm2_b,
+                          (const float *)w->concat3.layer_b, h->wc3_f, h->cs_c3, h->bc3_f, 256, D, s));
+    }
     const size_t Mc = (size_t)h->chunk_envs * h->N;
     const size_t Mp = ((Mc + 127) / 128) * 128; // padded so that tensor-map boxes never leave the allocation
+    if (h->ln_fold) { TRY(dev_alloc(h, &h->stats1, Mp * 4)); TRY(dev_alloc(h, &h->stats2, Mp * 4)); }
     TRY(dev_alloc(h, &h->h, Mp * D));
     TRY(dev_alloc(h, &h->y, Mp * D));
     TRY(dev_alloc(h, &h->qkv, Mp * 3 * D));
@@ -419,14 +492,14 @@ extern "C" int snb_jmid_denoise_agents(SnbJmid *h, const float *ctx, const float
         auto git = fx ? h->graphs.end() : h->graphs.find(key);
         if (git != h->graphs.end()) {
             SNB_CUDA_TRY(cudaGraphLaunch(git->second, s));
-            snb_count_launch(1 + n_iter * 26);   // kernels inside the replayed graph
+            snb_count_launch(1 + n_iter * (h->ln_fold ? 20 : 26));   // kernels inside the replayed graph
         } else if (!fx && h->use_graphs && s != nullptr && ++h->graph_uses[key] >= 2) {
             // second use of this shape: capture the sequence once, then replay it for every later chunk
             cudaGraph_t graph = nullptr;
             SNB_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
             float *res2 = nullptr;
             rc = chunk_sequence(h, P, n_steps, s, &res2);
-            snb_count_launch(-(1 + n_iter * 26)); // launches recorded during capture did not execute
+            snb_count_launch(-(1 + n_iter * (h->ln_fold ? 20 : 26))); // launches recorded during capture did not execute
             cudaError_t ce = cudaStreamEndCapture(s, &graph);
             if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
             if (ce != cudaSuccess) { snb_set_error("snb_jmid_denoise: graph capture failed: %s", cudaGetErrorString(ce)); return SNB_ECUDA; }
@@ -436,7 +509,7 @@ extern "C" int snb_jmid_denoise_agents(SnbJmid *h, const float *ctx, const float
             if (ce != cudaSuccess) { snb_set_error("snb_jmid_denoise: graph instantiate failed: %s", cudaGetErrorString(ce)); return SNB_ECUDA; }
             h->graphs[key] = exec;
             SNB_CUDA_TRY(cudaGraphLaunch(exec, s));
-            snb_count_launch(1 + n_iter * 26);
+            snb_count_launch(1 + n_iter * (h->ln_fold ? 20 : 26));
         } else {
             float *res2 = nullptr;
             if ((rc = chunk_sequence(h, P, n_steps, s, &res2))) return rc;

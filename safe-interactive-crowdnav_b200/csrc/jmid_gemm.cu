@@ -39,18 +39,37 @@ template <int BN> struct GemmCfg {
 };
 
 // one 32-column chunk of one accumulator row: + bias (+ReLU | ConcatSquash), result left in v[]
-template <int EPI>
+// Per-thread (= per accumulator row) state of the LayerNorm fold (see the comment above gemm2_bf16_tn_kernel).
+struct RowFold {
+    float rstd, nmr;       // FOLD: the A operand was z, not LN(z):  v = rstd * acc - rstd * mu * colsum[n] + bias'[n];  nmr = -rstd * mu
+    float r_rstd, r_mu;    // RES == 2: the residual is LN(z_res) recomputed from z_res and its row statistics
+    float sum, sumsq;      // RES != 0: statistics of the (bf16-rounded) row this thread writes, for the next consumer
+};
+
+template <int EPI, bool FOLD = false>
 __device__ __forceinline__ void epilogue_math(const uint32_t (&acc)[32], float (&v)[32], const float *s_bias, const GemmEpi &ep,
-                                              int col0_global, int ba)
+                                              int col0_global, int ba, const RowFold &rf = RowFold())
 {
     const float4 *b4 = reinterpret_cast<const float4 *>(s_bias);
+    if constexpr (FOLD) {
+        const float4 *c4 = reinterpret_cast<const float4 *>(ep.colsum + col0_global);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float4 b = b4[j];
-        v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
-        v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
-        v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
-        v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
+        for (int j = 0; j < 8; ++j) {
+            const float4 b = b4[j], c = __ldg(c4 + j);
+            v[4 * j + 0] = fmaf(__uint_as_float(acc[4 * j + 0]), rf.rstd, fmaf(rf.nmr, c.x, b.x));
+            v[4 * j + 1] = fmaf(__uint_as_float(acc[4 * j + 1]), rf.rstd, fmaf(rf.nmr, c.y, b.y));
+            v[4 * j + 2] = fmaf(__uint_as_float(acc[4 * j + 2]), rf.rstd, fmaf(rf.nmr, c.z, b.z));
+            v[4 * j + 3] = fmaf(__uint_as_float(acc[4 * j + 3]), rf.rstd, fmaf(rf.nmr, c.w, b.w));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 b = b4[j];
+            v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b.x;
+            v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b.y;
+            v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b.z;
+            v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b.w;
+        }
     }
     if constexpr (EPI == EPI_BIAS_RELU_BF16) {
 #pragma unroll
@@ -122,6 +141,87 @@ __device__ __forceinline__ void epilogue_drain(uint32_t t_addr, uint8_t *stg, co
             __syncwarp();
             if (lane == 0) { tc::tma_store_2d(tmC, stg, n0 + c, row0); tc::tma_store_commit(); }
         }
+    }
+}
+
+// + residual for one 32-column chunk: `rz` = the thread's 64 residual bf16 of these columns (4 x uint4 = 32 values), added in fp32;
+// RES == 2 recomputes LayerNorm(z_res) on the fly.  Then rounds to bf16, accumulates the row statistics of the ROUNDED values (what
+// the next GEMM will actually read) and leaves the packed pairs in pk[16].
+template <int RES>
+__device__ __forceinline__ void residual_pack(float (&v)[32], const uint4 (&rz)[4], const GemmEpi &ep, int col0_global, RowFold &rf,
+                                              uint32_t (&pk)[16])
+{
+    if constexpr (RES != 0) {
+        const uint32_t w[16] = {rz[0].x, rz[0].y, rz[0].z, rz[0].w, rz[1].x, rz[1].y, rz[1].z, rz[1].w,
+                                rz[2].x, rz[2].y, rz[2].z, rz[2].w, rz[3].x, rz[3].y, rz[3].z, rz[3].w};
+        if constexpr (RES == 2) {
+            const float4 *g4 = reinterpret_cast<const float4 *>(ep.res_gamma + col0_global);
+            const float4 *b4 = reinterpret_cast<const float4 *>(ep.res_beta + col0_global);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
+                const float z0 = __uint_as_float(w[2 * j] << 16), z1 = __uint_as_float(w[2 * j] & 0xffff0000u);
+                const float z2 = __uint_as_float(w[2 * j + 1] << 16), z3 = __uint_as_float(w[2 * j + 1] & 0xffff0000u);
+                v[4 * j + 0] += fmaf((z0 - rf.r_mu) * rf.r_rstd, g.x, b.x);
+                v[4 * j + 1] += fmaf((z1 - rf.r_mu) * rf.r_rstd, g.y, b.y);
+                v[4 * j + 2] += fmaf((z2 - rf.r_mu) * rf.r_rstd, g.z, b.z);
+                v[4 * j + 3] += fmaf((z3 - rf.r_mu) * rf.r_rstd, g.w, b.w);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                v[2 * j] += __uint_as_float(w[j] << 16);
+                v[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        pk[j] = tc::pack_bf16(v[2 * j], v[2 * j + 1]);
+        if constexpr (RES != 0) {
+            const float lo = __uint_as_float(pk[j] << 16), hi = __uint_as_float(pk[j] & 0xffff0000u);
+            rf.sum += lo + hi;
+            rf.sumsq = fmaf(lo, lo, fmaf(hi, hi, rf.sumsq));
+        }
+    }
+}
+
+// Drain of one warp's 32 rows x 128 columns (the pair kernel, BN = 256, bf16 output) with the LayerNorm fold: both 64-column chunks
+// unrolled so that the prefetched residual registers are indexed statically.
+template <int EPI, bool FOLD, int RES>
+__device__ __forceinline__ void epilogue_drain_fold(uint32_t t_addr, uint8_t *stg, const float *s_bias, const GemmEpi &ep,
+                                                    const CUtensorMap *tmC, int n0, int row0, int ba, int c_begin, int lane,
+                                                    RowFold &rf, const uint4 (&rz)[16])
+{
+    uint32_t ra[32], rb[32], pk[16];
+    float v[32];
+    tc::tmem_ld_32x32(t_addr + c_begin, ra);
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci) {
+        const int c = c_begin + ci * 64;
+        tc::tmem_ld_wait();
+        tc::tmem_ld_32x32(t_addr + c + 32, rb);
+        epilogue_math<EPI, FOLD>(ra, v, s_bias + c, ep, n0 + c, ba, rf);
+        {
+            const uint4 r4[4] = {rz[ci * 8 + 0], rz[ci * 8 + 1], rz[ci * 8 + 2], rz[ci * 8 + 3]};
+            residual_pack<RES>(v, r4, ep, n0 + c, rf, pk);
+        }
+        if (lane == 0) tc::tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *staging_slot(stg, lane, j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        tc::tmem_ld_wait();
+        if (ci == 0) tc::tmem_ld_32x32(t_addr + c + 64, ra);
+        epilogue_math<EPI, FOLD>(rb, v, s_bias + c + 32, ep, n0 + c + 32, ba, rf);
+        {
+            const uint4 r4[4] = {rz[ci * 8 + 4], rz[ci * 8 + 5], rz[ci * 8 + 6], rz[ci * 8 + 7]};
+            residual_pack<RES>(v, r4, ep, n0 + c + 32, rf, pk);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *staging_slot(stg, lane, 4 + j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) { tc::tma_store_2d(tmC, stg, n0 + c, row0); tc::tma_store_commit(); }
     }
 }
 
@@ -264,7 +364,17 @@ template <int BN> struct Gemm2Cfg {
     static constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;
 };
 
-template <int BN, int EPI>
+//
+// LayerNorm fold (FOLD / RES template parameters; BN = 256 only).  The post-norm encoder layer is  y = LN1(h + attn(h)),
+// h' = LN2(y + ff(y)).  Instead of a LayerNorm kernel between the GEMMs (two HBM passes per layer, 11.7 % of the r01 step):
+//   * a PRODUCING GEMM (out-proj, linear2; RES != 0) adds the residual in its epilogue, writes the PRE-norm row z (bf16) and the
+//     row's sum / sum of squares (of the rounded values, one float2 per (row, 128-column slice));  RES == 2: the residual itself is a
+//     LayerNorm output that was never materialised -- it is recomputed from the previous z and ITS statistics, gamma, beta;
+//   * a CONSUMING GEMM (in_proj, linear1, concat3; FOLD) multiplies z by W' = W . diag(gamma) (folded once at model load) and undoes
+//     the normalisation per row in its epilogue:  LN(z) W^T = rstd (z W'^T) - rstd mu colsum(W') + (beta W^T + b).
+// Each epilogue thread owns one accumulator row, so mu / rstd are per-thread scalars; the residual slice of the thread (256 B) is
+// prefetched into registers before the accumulator is waited for.
+template <int BN, int EPI, bool FOLD = false, int RES = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const GemmEpi ep, const int M, const int N, const int K)
@@ -372,17 +482,51 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int i = etid; i < BN; i += EPI_WARPS * 32) s_bias[i] = __ldg(ep.bias + n0 + i);
             tc::named_bar_sync(1, EPI_WARPS * 32);
 
+            // LayerNorm fold: this thread's row statistics and (RES) its 128-column residual slice, loaded before the accumulator wait
+            RowFold rf = RowFold();
+            uint4 rz[16];
+            {
+                const int row = (row0 + lane < M) ? row0 + lane : M - 1;
+                if constexpr (FOLD) {
+                    const float4 *sp = reinterpret_cast<const float4 *>(ep.stats_in + (size_t)row * 4);
+                    const float4 a = __ldg(sp), b = __ldg(sp + 1);
+                    const float mu = (a.x + a.z + b.x + b.z) * (1.0f / 512.0f);
+                    const float var = (a.y + a.w + b.y + b.w) * (1.0f / 512.0f) - mu * mu;
+                    rf.rstd = rsqrtf(fmaxf(var, 0.0f) + 1e-5f);
+                    rf.nmr = -rf.rstd * mu;
+                }
+                if constexpr (RES != 0) {
+                    const uint4 *rp = reinterpret_cast<const uint4 *>(ep.resid + (size_t)row * N + n0 + half * (BN / 2));
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) rz[j] = __ldg(rp + j);
+                    if constexpr (RES == 2) {
+                        const float4 *sp = reinterpret_cast<const float4 *>(ep.res_stats + (size_t)row * 4);
+                        const float4 a = __ldg(sp), b = __ldg(sp + 1);
+                        rf.r_mu = (a.x + a.z + b.x + b.z) * (1.0f / 512.0f);
+                        const float var = (a.y + a.w + b.y + b.w) * (1.0f / 512.0f) - rf.r_mu * rf.r_mu;
+                        rf.r_rstd = rsqrtf(fmaxf(var, 0.0f) + 1e-5f);
+                    }
+                }
+            }
             tc::mbar_wait(&tfull[acc], acc_phase);
             __syncwarp();                 // reconverge before the .sync.aligned TMEM loads
             tc::tc_fence_after();
             const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
-            epilogue_drain<EPI>(t_addr, stg, s_bias, ep, &tmC, n0, row0, ba, half * (BN / 2), (half + 1) * (BN / 2), lane);
+            if constexpr (FOLD || RES != 0) {
+                static_assert(BN == 256, "the LayerNorm fold is written for 256-column tiles (two 64-column chunks per warp)");
+                epilogue_drain_fold<EPI, FOLD, RES>(t_addr, stg, s_bias, ep, &tmC, n0, row0, ba, half * (BN / 2), lane, rf, rz);
+            } else {
+                epilogue_drain<EPI>(t_addr, stg, s_bias, ep, &tmC, n0, row0, ba, half * (BN / 2), (half + 1) * (BN / 2), lane);
+            }
             // every TMEM load of this warp has completed (last tmem_ld_wait inside): hand the accumulator back
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
                 if (leader) tc::mbar_arrive(&tempty[acc]);
                 else tc::mbar_arrive_cluster(tc::mapa_u32(&tempty[acc], 0));
+            }
+            if constexpr (RES != 0) {
+                if (row0 + lane < M) ep.stats_out[(size_t)(row0 + lane) * 4 + (n0 / BN) * 2 + half] = make_float2(rf.sum, rf.sumsq);
             }
         }
         if (lane == 0) tc::tma_store_wait<0>();
@@ -430,19 +574,22 @@ int launch_t(const GemmPlan *p, const GemmEpi *ep, int num_sms, cudaStream_t str
     return SNB_OK;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool FOLD = false, int RES = 0>
 int launch2_t(const GemmPlan *p, const GemmEpi *ep, int num_sms, cudaStream_t stream)
 {
     using Cfg = Gemm2Cfg<BN>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        attr_err = cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BN, EPI, FOLD, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     });
     SNB_CUDA_TRY(attr_err);
     const int tiles = ((p->M + 2 * BM - 1) / (2 * BM)) * (p->N / BN);
     const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
-    gemm2_bf16_tn_kernel<BN, EPI><<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p->tmA, p->tmB2, p->tmC, *ep, p->M, p->N, p->K);
+    if (FOLD) SNB_REQUIRE(ep->colsum && ep->stats_in && p->K == 512, SNB_EINVAL, "gemm: LayerNorm fold needs colsum / stats_in and K = 512");
+    if (RES) SNB_REQUIRE(ep->resid && ep->stats_out && p->N == 512 && (RES == 1 || (ep->res_stats && ep->res_gamma && ep->res_beta)), SNB_EINVAL,
+                         "gemm: residual epilogue needs resid / stats_out (N = 512) and, for a normalised residual, its stats / gamma / beta");
+    gemm2_bf16_tn_kernel<BN, EPI, FOLD, RES><<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p->tmA, p->tmB2, p->tmC, *ep, p->M, p->N, p->K);
     snb_count_launch();
     SNB_CUDA_TRY(cudaGetLastError());
     return SNB_OK;
@@ -458,6 +605,16 @@ bool use_pair_kernel()
 template <int BN>
 int launch_bn(const GemmPlan *p, int kind, const GemmEpi *ep, int num_sms, cudaStream_t stream)
 {
+    if (ep->fold || ep->res) {
+        SNB_REQUIRE(BN == 256 && use_pair_kernel(), SNB_EUNSUPPORTED, "gemm: the LayerNorm-fold epilogues exist for the CTA-pair kernel (N %% 256 == 0) only");
+        if (kind == EPI_BIAS_BF16 && ep->fold && !ep->res) return launch2_t<256, EPI_BIAS_BF16, true, 0>(p, ep, num_sms, stream);
+        if (kind == EPI_BIAS_RELU_BF16 && ep->fold && !ep->res) return launch2_t<256, EPI_BIAS_RELU_BF16, true, 0>(p, ep, num_sms, stream);
+        if (kind == EPI_CSL_BF16 && ep->fold && !ep->res) return launch2_t<256, EPI_CSL_BF16, true, 0>(p, ep, num_sms, stream);
+        if (kind == EPI_BIAS_BF16 && !ep->fold && ep->res == 1) return launch2_t<256, EPI_BIAS_BF16, false, 1>(p, ep, num_sms, stream);
+        if (kind == EPI_BIAS_BF16 && !ep->fold && ep->res == 2) return launch2_t<256, EPI_BIAS_BF16, false, 2>(p, ep, num_sms, stream);
+        snb_set_error("gemm: unsupported LayerNorm-fold combination (epilogue %d, fold %d, res %d)", kind, ep->fold, ep->res);
+        return SNB_EUNSUPPORTED;
+    }
     if (BN == 256 && use_pair_kernel() && kind != EPI_BIAS_F32) {
         switch (kind) {
         case EPI_BIAS_BF16: return launch2_t<256, EPI_BIAS_BF16>(p, ep, num_sms, stream);

@@ -29,6 +29,15 @@ struct GemmEpi {
     const float *hbias;     // [n_ba, tab_ld]
     int tab_ld;
     int tok_per_env, T, A;  // row m -> b = m / tok_per_env, r = (m % tok_per_env) / T, a = r % A, ba = b*A + a
+    // LayerNorm fold (jmid_gemm.cu, CTA-pair kernel): all NULL / 0 = plain epilogue
+    int fold;                 // 1: the A operand is a pre-norm z; `bias` is beta W^T + b, `colsum` = colsum(W diag(gamma)), `stats_in` [M,4] of z
+    int res;                  // 1: + resid (bf16 [M,N]);  2: + LayerNorm(resid) from res_stats / res_gamma / res_beta;  both write stats_out
+    const float *colsum;
+    const float2 *stats_in;
+    const bf16 *resid;
+    const float2 *res_stats;
+    const float *res_gamma, *res_beta;
+    float2 *stats_out;        // [M,4] (sum, sum of squares) per 128-column slice of the written row
 };
 
 struct GemmPlan {
@@ -60,6 +69,9 @@ int snb_attn_small_launch(const bf16 *qkv, bf16 *out, int n_seq, int T, cudaStre
 
 // ---- elementwise kernels (jmid_kernels.cu) ----
 int snb_k_f32_to_bf16(const float *src, bf16 *dst, size_t n, cudaStream_t s);
+// LayerNorm(gamma, beta) folded into the consuming Linear(W [N,K], bias): Wf = bf16(W diag(gamma)), colsum(Wf), bias + beta W^T
+int snb_k_fold_ln(const float *W, const float *gamma, const float *beta, const float *bias, bf16 *Wf, float *colsum, float *bias_f,
+                  int N, int K, cudaStream_t s);
 // ctx-dependent, iteration-invariant part of the 4 hyper networks: gc[ba, 898] = Wg[:,3:] ctx[ba] + bg, bc = Wb[:,3:] ctx[ba]
 struct HyperW { const float *gate_w, *gate_b, *bias_w; int dout; }; // gate_w / bias_w are [dout, 259]
 int snb_k_hyper_ctx(const HyperW *layers4, const float *ctx, float *gc, float *bc, int n_ba, cudaStream_t s);

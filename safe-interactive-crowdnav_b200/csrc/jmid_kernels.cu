@@ -13,6 +13,31 @@ __global__ void f32_to_bf16_kernel(const float *__restrict__ src, bf16 *__restri
     if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
 }
 
+// LayerNorm folded into the consuming nn.Linear (model load time): W'[n,k] = bf16(W[n,k] gamma[k]); colsum[n] = sum_k W'[n,k] (of the
+// ROUNDED values: the GEMM multiplies by those); bias'[n] = bias[n] + sum_k beta[k] W[n,k].  One block per output row n.
+__global__ void fold_ln_kernel(const float *__restrict__ W, const float *__restrict__ gamma, const float *__restrict__ beta,
+                               const float *__restrict__ bias, bf16 *__restrict__ Wf, float *__restrict__ colsum, float *__restrict__ bias_f, int K)
+{
+    const int n = blockIdx.x;
+    float cs = 0.0f, bb = 0.0f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const float w = W[(size_t)n * K + k];
+        const bf16 wf = __float2bfloat16_rn(w * gamma[k]);
+        Wf[(size_t)n * K + k] = wf;
+        cs += __bfloat162float(wf);
+        bb = fmaf(beta[k], w, bb);
+    }
+    __shared__ float s_a[4], s_b[4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { cs += __shfl_xor_sync(0xffffffffu, cs, o); bb += __shfl_xor_sync(0xffffffffu, bb, o); }
+    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = cs; s_b[threadIdx.x >> 5] = bb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        colsum[n] = (s_a[0] + s_a[1]) + (s_a[2] + s_a[3]);
+        bias_f[n] = bias[n] + ((s_b[0] + s_b[1]) + (s_b[2] + s_b[3]));
+    }
+}
+
 struct Hyper4 { HyperW l[4]; };
 
 // one block per (ba); threads stride over the 898 output columns; ctx row staged in shared memory
@@ -202,6 +227,15 @@ __global__ void integrate_kernel(const float *__restrict__ vel, const float *__r
 }
 
 } // namespace
+
+int snb_k_fold_ln(const float *W, const float *gamma, const float *beta, const float *bias, bf16 *Wf, float *colsum, float *bias_f,
+                  int N, int K, cudaStream_t s)
+{
+    fold_ln_kernel<<<N, 128, 0, s>>>(W, gamma, beta, bias, Wf, colsum, bias_f, K);
+    snb_count_launch();
+    SNB_CUDA_TRY(cudaGetLastError());
+    return SNB_OK;
+}
 
 int snb_k_f32_to_bf16(const float *src, bf16 *dst, size_t n, cudaStream_t s)
 {
