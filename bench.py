@@ -597,12 +597,12 @@ def kernel_rooflines(den, kt, pk, B, NS, ms_per_step):
     peak = pk["tf_burst"]
     n_chunks = (B + chunk - 1) // chunk
     attn_share = t_attn * 3 * NS * n_chunks / ms_per_step
-    roof = {"kernel": "attn_fwd_kernel (flash attention: tcgen05 SS MMAs, S / O in TMEM, P through swizzled shared memory, persistent)", "bound": "tensor",
+    roof = {"kernel": "attn_fwd_kernel (flash attention: tcgen05 SS MMAs, S / O in TMEM, P through swizzled shared memory, O out by TMA store, persistent)", "bound": "tensor",
             "achieved": fl_attn / (t_attn * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
             "frac": fl_attn / (t_attn * 1e-3) / 1e12 / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this very shape (ncu --set full, profiles/r01_ncu_attn_persistent_chunk512.txt):
-            # 2.523 GB + 0.819 GB against 2.517 GB (QKV) + 0.839 GB (out) algorithmic -- K / V re-reads by the 7 query-pair items hit L2
-            "traffic": 3341.6e6 if (chunk == 512 and N == 1600) else None, "traffic_unit": "bytes per launch",
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this very shape (ncu --set full, profiles/r02_ncu_attn_tma_epilogue_chunk512.txt):
+            # 2.534 GB + 0.818 GB against 2.517 GB (QKV) + 0.839 GB (out) algorithmic -- K / V re-reads by the 7 query-pair items hit L2
+            "traffic": 3352.2e6 if (chunk == 512 and N == 1600) else None, "traffic_unit": "bytes per launch",
             "peak_source": f"{pk['src']} (burst: kernel timed alone, before the long timed region)",
             "flops_per_launch": fl_attn, "avg_launch_ms": t_attn, "launches_per_step": 3 * NS * n_chunks,
             "share_of_step": attn_share, "share_note": "alone-launch time x launches / step time; inside the power-capped step the kernel runs ~20 % slower",

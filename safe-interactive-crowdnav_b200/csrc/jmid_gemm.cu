@@ -199,22 +199,33 @@ __device__ __forceinline__ void epilogue_drain_fold(uint32_t t_addr, uint8_t *st
 #pragma unroll
     for (int ci = 0; ci < 2; ++ci) {
         const int c = c_begin + ci * 64;
+        // The residual chunk (32 rows x 128 B) was prefetched COALESCED (lane = 16-byte piece (lane & 7) of row 4 i + (lane >> 3)): it is
+        // transposed to "thread = row" through this warp's staging tile, which the previous TMA store must have finished reading.
+        uint4 mine[8];
+        if (lane == 0) tc::tma_store_wait_read<0>();
+        __syncwarp();
+        if constexpr (RES != 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) *staging_slot(stg, i * 4 + (lane >> 3), lane & 7) = rz[ci * 8 + i];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mine[j] = *staging_slot(stg, lane, j);
+            __syncwarp();
+        }
         tc::tmem_ld_wait();
         tc::tmem_ld_32x32(t_addr + c + 32, rb);
         epilogue_math<EPI, FOLD>(ra, v, s_bias + c, ep, n0 + c, ba, rf);
         {
-            const uint4 r4[4] = {rz[ci * 8 + 0], rz[ci * 8 + 1], rz[ci * 8 + 2], rz[ci * 8 + 3]};
+            const uint4 r4[4] = {mine[0], mine[1], mine[2], mine[3]};
             residual_pack<RES>(v, r4, ep, n0 + c, rf, pk);
         }
-        if (lane == 0) tc::tma_store_wait_read<0>();
-        __syncwarp();
 #pragma unroll
         for (int j = 0; j < 4; ++j) *staging_slot(stg, lane, j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         tc::tmem_ld_wait();
         if (ci == 0) tc::tmem_ld_32x32(t_addr + c + 64, ra);
         epilogue_math<EPI, FOLD>(rb, v, s_bias + c + 32, ep, n0 + c + 32, ba, rf);
         {
-            const uint4 r4[4] = {rz[ci * 8 + 4], rz[ci * 8 + 5], rz[ci * 8 + 6], rz[ci * 8 + 7]};
+            const uint4 r4[4] = {mine[4], mine[5], mine[6], mine[7]};
             residual_pack<RES>(v, r4, ep, n0 + c + 32, rf, pk);
         }
 #pragma unroll
@@ -496,9 +507,13 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     rf.nmr = -rf.rstd * mu;
                 }
                 if constexpr (RES != 0) {
-                    const uint4 *rp = reinterpret_cast<const uint4 *>(ep.resid + (size_t)row * N + n0 + half * (BN / 2));
+                    // coalesced: per instruction the warp reads 4 rows x 128 B (four full lines) instead of 16 B from 32 different rows
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) rz[j] = __ldg(rp + j);
+                    for (int j = 0; j < 16; ++j) {
+                        int rr = row0 + (j & 7) * 4 + (lane >> 3);
+                        if (rr >= M) rr = M - 1;
+                        rz[j] = __ldg(reinterpret_cast<const uint4 *>(ep.resid + (size_t)rr * N + n0 + half * (BN / 2) + (j >> 3) * 64) + (lane & 7));
+                    }
                     if constexpr (RES == 2) {
                         const float4 *sp = reinterpret_cast<const float4 *>(ep.res_stats + (size_t)row * 4);
                         const float4 a = __ldg(sp), b = __ldg(sp + 1);
