@@ -1,4 +1,11 @@
 /*
+ * The ORCA arithmetic restated here follows the RVO2 Library (v2.0.x: Agent.cpp, KdTree.cpp, RVOSimulator.cpp),
+ *   Copyright 2008 University of North Carolina at Chapel Hill,
+ *   licensed under the Apache License, Version 2.0 (http://www.apache.org/licenses/LICENSE-2.0).
+ * RVO2 is distributed on an "AS IS" BASIS, WITHOUT WARRANTIES OR CONDITIONS OF ANY KIND; see the License for the specific
+ * language governing permissions and limitations.  <https://gamma.cs.unc.edu/RVO2/>   This file is a derived restatement, not a copy.
+ */
+/*
  * oracle/rvo2_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.  PARITY UNPINNED.
  * See rvo2_oracle.h for provenance.  Every function names the RVO2 routine
  *  and the reference call site it serves.

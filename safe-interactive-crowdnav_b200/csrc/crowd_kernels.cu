@@ -13,6 +13,13 @@
 // Numerics: this file is compiled with -fmad=false.  ORCA runs in fp32 exactly where Python-RVO2 does (every
 // float op is a single IEEE op in the order of RVO2's Agent.cpp) so it is bit-identical to oracle/rvo2_oracle.c;
 // everything else is fp64 like the reference's Python, with explicit fma() only where numpy's BLAS dot fuses.
+/*
+ * The ORCA parts of this file (half-plane construction, linearProgram1-3, neighbour selection, obstacle BSP walk) follow the RVO2 Library (v2.0.x: Agent.cpp, KdTree.cpp, RVOSimulator.cpp),
+ *   Copyright 2008 University of North Carolina at Chapel Hill,
+ *   licensed under the Apache License, Version 2.0 (http://www.apache.org/licenses/LICENSE-2.0).
+ * RVO2 is distributed on an "AS IS" BASIS, WITHOUT WARRANTIES OR CONDITIONS OF ANY KIND; see the License for the specific
+ * language governing permissions and limitations.  <https://gamma.cs.unc.edu/RVO2/>   This file is a derived restatement, not a copy.
+ */
 #include <cfloat>
 #include <cmath>
 #include <cstring>
