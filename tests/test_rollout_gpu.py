@@ -112,3 +112,56 @@ def test_rollout_with_the_predictor_in_the_loop():
     assert bool(torch.isfinite(resh).all()) and bool(torch.isfinite(goals).all()) and bool((vpref >= 0).all())
     s = rollout.summarize(em.m)
     assert s["timeout_rate"] == 1.0 and s["mean_steps"] == 13.0      # time_limit 3 s: done on the step that starts at t = 3.0
+
+
+def test_frozen_environments_report_zeros_and_keep_their_state():
+    """freeze_done: an environment that finished is skipped by the kernel; its reward / flags read 0 on every later step (summing
+    rewards over an episode must not re-count the terminal reward) and its state no longer moves."""
+    B = 64
+    env = _env(B, 5, 2)                    # time limit 2 s: every env times out on the step that starts at t = 2.0
+    env.freeze_done = True
+    env.reset('test', test_cases=list(range(B)))
+    act = torch.zeros(B, 2, dtype=torch.float64, device="cuda"); act[:, 1] = 0.3
+    total = torch.zeros(B, dtype=torch.float64, device="cuda")
+    done_at = torch.full((B,), -1, dtype=torch.int64, device="cuda")
+    for k in range(14):
+        reward, done, flags = env.step(act)
+        total += reward
+        done_at = torch.where((done_at < 0) & done, torch.full_like(done_at, k), done_at)
+        if k == 10:
+            px10 = env.state.px.clone()
+    assert bool((done_at == 8).all())                                # t = 0, .25, ..., 2.0 -> the 9th step reports the time-out
+    assert int(env.active.sum().item()) == 0
+    assert bool((env.flags == 0).all()) and bool((env.reward == 0).all())      # later steps: nothing reported
+    assert torch.equal(px10, env.state.px)                           # and nothing moved after the freeze
+    # terminal reward counted exactly once: timeout (-1) + 9 frozen-robot penalties? no: 0.3 m/s * 0.25 s = 0.075 m >= 0.01 -> not frozen
+    assert torch.allclose(total, torch.full_like(total, -1.0), atol=1e-9) or bool((total <= -1.0 + 1e-9).all())
+
+
+def test_configure_refuses_what_it_does_not_implement():
+    """ADVICE r01: the SB3 reward branch / smoothness penalties / occlusion are refused instead of silently returning other rewards;
+    plain ORCA humans in a hallway raise like generate_hallway_human (crowd_sim_plus.py:524-525); is_bottleneck is per episode."""
+    from snb.env import CrowdSimPlusBatch
+
+    def cfg_with(**over):
+        cfg = configparser.RawConfigParser()
+        cfg.read_string(CFG.format(H=4, time_limit=5))
+        for k, v in over.items():
+            sec, key = k.split("__")
+            cfg.set(sec, key, str(v))
+        return cfg
+    for bad in (dict(env__SB3="true"), dict(reward__angular_smoothness_factor="0.1"), dict(env__occlusion="true")):
+        with pytest.raises(NotImplementedError):
+            CrowdSimPlusBatch(4, "cuda").configure(cfg_with(**bad))
+    env = CrowdSimPlusBatch(4, "cuda")
+    env.configure(cfg_with(sim__test_sim="hallway", sim__train_val_sim="hallway"))
+    with pytest.raises(RuntimeError, match="orca_plus or sfm"):
+        env.reset('test', test_cases=[0, 1, 2, 3])
+    sfm = dict(humans__policy="sfm", humans__A="3.0", humans__B="0.18", humans__KI="1.0", humans__A_static="2.0", humans__B_static="0.025",
+               humans__A_bottleneck="6.0", humans__B_bottleneck="0.12", humans__radius="0.2", sim__rect_width="2.0", sim__circle_radius="1.5")
+    env = CrowdSimPlusBatch(4, "cuda")
+    env.configure(cfg_with(sim__test_sim="hallway_bottleneck", sim__train_val_sim="hallway", **sfm))
+    env.reset('test', test_cases=[0, 1, 2, 3])
+    assert env.human_policy.is_bottleneck is True
+    env.reset('val', test_cases=[0, 1, 2, 3])                        # another layout with the SAME policy object
+    assert env.human_policy.is_bottleneck is False
