@@ -123,10 +123,12 @@ def test_frozen_environments_report_zeros_and_keep_their_state():
     env.reset('test', test_cases=list(range(B)))
     act = torch.zeros(B, 2, dtype=torch.float64, device="cuda"); act[:, 1] = 0.3
     total = torch.zeros(B, dtype=torch.float64, device="cuda")
+    total_live = torch.zeros(B, dtype=torch.float64, device="cuda")   # rewards of the steps up to and including the terminal one
     done_at = torch.full((B,), -1, dtype=torch.int64, device="cuda")
     for k in range(14):
         reward, done, flags = env.step(act)
         total += reward
+        total_live += reward * (done_at < 0)
         done_at = torch.where((done_at < 0) & done, torch.full_like(done_at, k), done_at)
         if k == 10:
             px10 = env.state.px.clone()
@@ -134,8 +136,7 @@ def test_frozen_environments_report_zeros_and_keep_their_state():
     assert int(env.active.sum().item()) == 0
     assert bool((env.flags == 0).all()) and bool((env.reward == 0).all())      # later steps: nothing reported
     assert torch.equal(px10, env.state.px)                           # and nothing moved after the freeze
-    # terminal reward counted exactly once: timeout (-1) + 9 frozen-robot penalties? no: 0.3 m/s * 0.25 s = 0.075 m >= 0.01 -> not frozen
-    assert torch.allclose(total, torch.full_like(total, -1.0), atol=1e-9) or bool((total <= -1.0 + 1e-9).all())
+    assert torch.equal(total, total_live) and bool((total <= -1.0 + 1e-9).all())   # the terminal reward (time-out, -1) is counted once
 
 
 def test_configure_refuses_what_it_does_not_implement():
