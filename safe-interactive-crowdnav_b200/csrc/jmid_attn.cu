@@ -123,7 +123,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #endif
 
     if (warp < 4) {
-        setmaxnreg_dec<88>();
+        setmaxnreg_dec<120>();
         if (warp == 0 && lane == 0) {
             // ===================== TMA producer =====================
             int c = 0;                                   // running index into the K0, K1, V0, K2, V1, ... sequence (all items)
@@ -252,7 +252,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           }
         }
     } else {
-        setmaxnreg_inc<208>();
+        setmaxnreg_inc<192>();
         // ===================== softmax / correction / epilogue of tile t =====================
         const int t = (warp - 4) >> 2;
         const uint32_t tmem_base = *tmem_slot;
