@@ -84,7 +84,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     uint64_t *kv_full = bars + 2, *kv_empty = bars + 5;    // [3] per ring slot
     uint64_t *s_full = bars + 8, *s_free = bars + 10, *p_ready = bars + 12, *pv_done = bars + 14;   // [2] per tile
     uint64_t *q_empty = bars + 16, *o_free = bars + 18;    // [2] per tile: Q_t may be refilled / O_t may be overwritten (next work item)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 20);
+    uint64_t *lag = bars + 20;                             // tile A -> tile B: "half of my first block is done" (de-phases the two softmaxes)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 21);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int n_tok = args.n_tok;
@@ -111,6 +112,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             tc::mbar_init(&q_full[s], 1); tc::mbar_init(&q_empty[s], 1); tc::mbar_init(&o_free[s], 128);
             tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_free[s], 128); tc::mbar_init(&p_ready[s], 128); tc::mbar_init(&pv_done[s], 1);
         }
+        tc::mbar_init(lag, 128);
         for (int s = 0; s < ATTN_RING; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1); }
         tc::fence_barrier_init();
     }
@@ -266,10 +268,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         const int sw = row_in_tile & 7;
         const float c = args.scale_log2;
         int g = 0;                    // iterations of this tile so far: every per-tile barrier completes one phase per iteration
+        int n_lag = 0;                // items with two tiles so far (phase of `lag`)
         for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
             int q0, head, env; bool has_b;
             decode(w, q0, head, env, has_b);
             if (t == 1 && !has_b) continue;
+#ifndef SNB_ATTN_NO_LAG
+            // De-phase the tiles.  Both softmaxes share the four XU (MUFU) pipes; started together they stay in phase for the whole item,
+            // each exponential phase then runs at half the MUFU rate and the pipes idle during both tiles' load / max / store phases.
+            // Tile B therefore starts its item half a block after tile A; nothing else couples the two, so the offset persists.
+            if (t == 1) tc::mbar_wait(lag, n_lag & 1);
+            if (has_b) ++n_lag;
+#endif
             float m_used = -INFINITY; // running max the exponents are taken against (raw score units)
             float l = 0.0f;
             // one 128-key block.  RAGGED is a compile-time flag: ptxas if-converts the masking of keys that do not exist into 128 ISETP +
@@ -376,6 +386,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 }
                 store(s0, 0, 0);
                 exp_pack(s1); store(s1, 0, 4);
+#ifndef SNB_ATTN_NO_LAG
+                if (t == 0 && j == 0 && has_b) tc::mbar_arrive(lag);
+#endif
                 exp_pack(s2); store(s2, 1, 0);
                 exp_pack(s3);
                 ATTN_TRACE(t, j, 3);
