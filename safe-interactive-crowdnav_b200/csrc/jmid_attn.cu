@@ -66,6 +66,9 @@ template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile
 #ifndef SNB_ATTN_POLY_EVERY
 #define SNB_ATTN_POLY_EVERY 4
 #endif
+#ifndef SNB_ATTN_LAG_AT
+#define SNB_ATTN_LAG_AT 1      // tile B starts when tile A has finished this many quarters (+1) of its first block's exponentials
+#endif
 constexpr int ATTN_THREADS = 384;
 constexpr int ATTN_RING = 3;
 constexpr int ATTN_SMEM = TILE_BYTES * (2 + 2 + ATTN_RING) + 1024 + 256;
@@ -386,13 +389,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 }
                 store(s0, 0, 0);
                 exp_pack(s1); store(s1, 0, 4);
-#ifndef SNB_ATTN_NO_LAG
+#if !defined(SNB_ATTN_NO_LAG) && SNB_ATTN_LAG_AT == 1
                 if (t == 0 && j == 0 && has_b) tc::mbar_arrive(lag);
 #endif
                 exp_pack(s2); store(s2, 1, 0);
+#if !defined(SNB_ATTN_NO_LAG) && SNB_ATTN_LAG_AT == 2
+                if (t == 0 && j == 0 && has_b) tc::mbar_arrive(lag);
+#endif
                 exp_pack(s3);
                 ATTN_TRACE(t, j, 3);
                 store(s3, 1, 4);
+#if !defined(SNB_ATTN_NO_LAG) && SNB_ATTN_LAG_AT == 3
+                if (t == 0 && j == 0 && has_b) tc::mbar_arrive(lag);
+#endif
                 {
                     float a0, a1, b0, b1;
                     tc::f2_unpack(sumA, a0, a1);
