@@ -201,6 +201,7 @@ struct CrowdParams {
     double *next_robot; // full_step == 2: [B, n_actions, 2] constrained next robot position (optional)
     int thread_mode;    // phase 1: 0 = one warp per human (small launches), 1 = one thread per human (large batches)
     int fast_lines;     // thread mode, plain ORCA: half-planes of every thread in shared memory (this many per thread), no local memory
+    int lp3_mode;       // warp-owns-environments kernel: 0 = lp3_warp (loop per half-plane), 1 = lp3_warp_skip (ballot scans)
 };
 
 struct Line { float px, py, dx, dy; };
@@ -322,6 +323,94 @@ __device__ void lp3_warp(const Line &my, int n, int numObstLines, int beginLine,
             if (lp2_warp(mine, np, radius, -li.dy, li.dx, true, rx, ry, lane) < np) { rx = tx; ry = ty; }
             distance = det2(li.dx, li.dy, li.px - rx, li.py - ry);
         }
+    }
+}
+
+__device__ __forceinline__ float redux_min(float v) { float r; asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float redux_max(float v) { float r; asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r; }
+
+// linearProgram3 for the warp-owns-environments kernel.  Same arithmetic per half-plane as lp3_warp / lp3_serial, but the two
+// sequential scans ("next half-plane the current point violates") are one ballot each instead of one loop trip per half-plane:
+// the point only moves when a linearProgram1 succeeds, so every half-plane between two moves is tested against the same point
+// and the first set bit of the ballot is exactly the half-plane the sequential loop would stop at.  Half-planes are read from
+// shared memory as broadcasts (L[j * 32], the failing human's column of the warp's line store), min / max of the LP1 scan are
+// single CREDUX instructions.  `scratch` = 32 float4 of per-warp shared memory for the projected half-planes.
+__device__ void lp3_warp_skip(const float4 *L, int n, int beginLine, float radius, float &rx, float &ry, int lane, float4 *scratch)
+{
+    Line my; my.px = 0.f; my.py = 0.f; my.dx = 1.f; my.dy = 0.f;
+    if (lane < n) { const float4 v = L[lane * 32]; my.px = v.x; my.py = v.y; my.dx = v.z; my.dy = v.w; }
+    const unsigned lt = (1u << lane) - 1u;
+    float distance = 0.0f;
+    int i = beginLine;
+    while (true) {
+        const bool viol = lane >= i && lane < n && det2(my.dx, my.dy, my.px - rx, my.py - ry) > distance;
+        const unsigned vm = __ballot_sync(FULL, viol);
+        if (!vm) break;
+        i = __ffs(vm) - 1;
+        Line li; { const float4 v = L[i * 32]; li.px = v.x; li.py = v.y; li.dx = v.z; li.dy = v.w; }
+        bool have = false;
+        Line pl = my;
+        if (lane < i) {
+            const float determinant = det2(li.dx, li.dy, my.dx, my.dy);
+            have = true;
+            if (fabsf(determinant) <= RVO_EPSILON) {
+                if (dot2(li.dx, li.dy, my.dx, my.dy) > 0.0f) have = false;
+                else { pl.px = 0.5f * (li.px + my.px); pl.py = 0.5f * (li.py + my.py); }
+            } else {
+                const float sv = det2(my.dx, my.dy, li.px - my.px, li.py - my.py) / determinant;
+                pl.px = li.px + sv * li.dx; pl.py = li.py + sv * li.dy;
+            }
+            if (have) {
+                const float vx = my.dx - li.dx, vy = my.dy - li.dy;
+                const float inv = 1.0f / sqrtf(dot2(vx, vy, vx, vy));
+                pl.dx = vx * inv; pl.dy = vy * inv;
+            }
+        }
+        const unsigned hm = __ballot_sync(FULL, have);
+        const int np = __popc(hm);
+        if (have) scratch[__popc(hm & lt)] = make_float4(pl.px, pl.py, pl.dx, pl.dy);
+        __syncwarp();
+        Line mine; mine.px = 0.f; mine.py = 0.f; mine.dx = 1.f; mine.dy = 0.f;
+        if (lane < np) { const float4 v = scratch[lane]; mine.px = v.x; mine.py = v.y; mine.dx = v.z; mine.dy = v.w; }
+        // linearProgram2(projected, radius, (-li.dy, li.dx), directionOpt = true)
+        const float ox = -li.dy, oy = li.dx;
+        float qx = ox * radius, qy = oy * radius;
+        bool ok = true;
+        int k = 0;
+        while (true) {
+            const bool vv = lane >= k && lane < np && det2(mine.dx, mine.dy, mine.px - qx, mine.py - qy) > 0.0f;
+            const unsigned m2 = __ballot_sync(FULL, vv);
+            if (!m2) break;
+            k = __ffs(m2) - 1;
+            Line lk; { const float4 v = scratch[k]; lk.px = v.x; lk.py = v.y; lk.dx = v.z; lk.dy = v.w; }
+            const float dotProduct = dot2(lk.px, lk.py, lk.dx, lk.dy);
+            const float discriminant = dotProduct * dotProduct + radius * radius - dot2(lk.px, lk.py, lk.px, lk.py);
+            if (discriminant < 0.0f) { ok = false; break; }
+            const float sq = sqrtf(discriminant);
+            float tLeft = -dotProduct - sq;
+            float tRight = -dotProduct + sq;
+            float myL = -INFINITY, myR = INFINITY;
+            bool pfail = false;
+            if (lane < k) {
+                const float denominator = det2(lk.dx, lk.dy, mine.dx, mine.dy);
+                const float numerator = det2(mine.dx, mine.dy, lk.px - mine.px, lk.py - mine.py);
+                if (fabsf(denominator) <= RVO_EPSILON) { if (numerator < 0.0f) pfail = true; }
+                else {
+                    const float t = numerator / denominator;
+                    if (denominator >= 0.0f) myR = t; else myL = t;
+                }
+            }
+            tRight = fminf(tRight, redux_min(myR));
+            tLeft = fmaxf(tLeft, redux_max(myL));
+            if ((__any_sync(FULL, pfail) != 0) || (tLeft > tRight)) { ok = false; break; }
+            if (dot2(ox, oy, lk.dx, lk.dy) > 0.0f) { qx = lk.px + tRight * lk.dx; qy = lk.py + tRight * lk.dy; }
+            else { qx = lk.px + tLeft * lk.dx; qy = lk.py + tLeft * lk.dy; }
+            ++k;
+        }
+        __syncwarp();                                       // everybody has read `scratch` before the next projection overwrites it
+        if (ok) { rx = qx; ry = qy; }
+        distance = det2(li.dx, li.dy, li.px - rx, li.py - ry);
+        ++i;
     }
 }
 
@@ -1711,9 +1800,13 @@ __global__ void __launch_bounds__(32 * FW_WARPS) crowd_orca_warp_kernel(const Cr
         const int n = __shfl_sync(FULL, n_l, src), begin = __shfl_sync(FULL, fail, src);
         const float r = __shfl_sync(FULL, spd, src);
         float rx = __shfl_sync(FULL, fx, src), ry = __shfl_sync(FULL, fy, src);
-        Line my; my.px = 0.f; my.py = 0.f; my.dx = 1.f; my.dy = 0.f;
-        if (lane < n) my = SmemLinesT<32>{s_lines + src}[lane];
-        lp3_warp(my, n, 0, begin, r, rx, ry, lane, scratch);
+        if (P.lp3_mode == 0) {
+            Line my; my.px = 0.f; my.py = 0.f; my.dx = 1.f; my.dy = 0.f;
+            if (lane < n) my = SmemLinesT<32>{s_lines + src}[lane];
+            lp3_warp(my, n, 0, begin, r, rx, ry, lane, scratch);
+        } else {
+            lp3_warp_skip(s_lines + src, n, begin, r, rx, ry, lane, reinterpret_cast<float4 *>(scratch));
+        }
         if (lane == src) { fx = rx; fy = ry; }
     }
     const double c0 = (double)fx, c1 = (double)fy;
@@ -1890,6 +1983,10 @@ static int launch_crowd(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const S
         cfg->max_neighbors >= 1 && cfg->max_neighbors <= FAST_LCAP && !getenv("SNB_CROWD_NO_FAST") &&
         crowd_smem_bytes(P.epc, st->H, st->E, P.n_seg, cfg->max_neighbors) <= 96 * 1024)
         P.fast_lines = cfg->max_neighbors;
+    {
+        const char *m = getenv("SNB_CROWD_LP3");
+        P.lp3_mode = m ? atoi(m) : 1;
+    }
 
     // the barrier-free kernel: plain ORCA, no walls, the simulator's single robot, update / policy-only (not the what-if look-ahead)
     if (P.fast_lines && P.n_seg == 0 && st->E == 1 && full_step != 2 && st->H <= 32 && !getenv("SNB_CROWD_NO_WARPOWN")) {
