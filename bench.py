@@ -544,6 +544,22 @@ def sim_only_lines(dev, pk, cfg_text):
                             "frac": alg / (t_step * 1e-3) / 1e9 / pk["hbm_gbs"], "fp64_state_gbs": moved / (t_step * 1e-3) / 1e9,
                             "note": "state fits L2: latency / occupancy bound" if moved < 100e6 else "state >> L2"},
                "reset_on_device_ms": t_reset, "reset_envs_per_s": B / (t_reset * 1e-3)}
+        if B >= (1 << 20):
+            # the cost of a step follows the crowd: the launches timed above are the first steps after reset + starts_moving, when all
+            # humans meet in the middle of the circle and a third of them need linearProgram3.  One whole 100-step episode, every launch
+            # timed on its own with the L2 flushed, gives the figure a rollout sees.
+            env.reset('test', test_cases=cases)
+            ep = []
+            for _ in range(100):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); env.step(act); b.record()
+                torch.cuda.synchronize()
+                ep.append(a.elapsed_time(b))
+            ep = np.asarray(ep)
+            rec["episode_100_steps"] = {"env_steps_per_s_mean": B / (float(ep.mean()) * 1e-3), "launch_ms_mean": float(ep.mean()),
+                                        "launch_ms_min": float(ep.min()), "launch_ms_max": float(ep.max()), "slowest_step": int(ep.argmax()),
+                                        "launch_ms_by_decade": [round(float(ep[k:k + 10].mean()), 3) for k in range(0, 100, 10)]}
         if B <= 4096:
             A = 31
             acts = torch.zeros(B, A, 2, dtype=torch.float64, device=dev); acts[:, 1:, 1] = 0.5

@@ -986,7 +986,9 @@ __device__ void lp3_serial(const LA &lines, int n, int numObstLines, int beginLi
     }
 }
 
-__device__ void orca_predict_thread(const CrowdParams &P, const Tile &T, int e, int i, int genv, float &out_vx, float &out_vy)
+// (goal and v_pref of the human are parameters: the warp-owns-environments kernel keeps them in registers, not in the tile)
+__device__ void orca_predict_thread(const CrowdParams &P, const Tile &T, int e, int i, int genv, double goal_x, double goal_y, double v_pref,
+                                    float &out_vx, float &out_vy)
 {
     const SnbPolicyCfg &cfg = P.cfg;
     const int H = P.st.H, E = P.st.E;
@@ -995,18 +997,18 @@ __device__ void orca_predict_thread(const CrowdParams &P, const Tile &T, int e, 
     const double dpx = T.px[k], dpy = T.py[k];
     const float px = (float)dpx, py = (float)dpy, vx = (float)T.vx[k], vy = (float)T.vy[k];
     const float radius = (float)(T.rad[k] + 0.01 + cfg.safety_space);   // orca.py:100
-    const float maxSpeed = (float)T.vpref[k];
+    const float maxSpeed = (float)v_pref;
     const float neighborDist = (float)cfg.neighbor_dist;
     const float timeHorizon = (float)cfg.time_horizon, timeHorizonObst = (float)cfg.time_horizon_obst;
     const float timeStep = (float)cfg.time_step;
     const int maxNeighbors = cfg.max_neighbors;
 
     // preferred velocity in double, then narrowed (orca.py:113-123 / orca_plus.py:68-79)
-    const double dvx = T.gx[k] - dpx, dvy = T.gy[k] - dpy;
+    const double dvx = goal_x - dpx, dvy = goal_y - dpy;
     const double speed = sqrt(fma(dvy, dvy, dvx * dvx)); // np.linalg.norm: BLAS dot fuses
     double pvx, pvy;
     if (cfg.policy == SNB_POLICY_ORCA_PLUS) {
-        const double vp = T.vpref[k] - 1e-3;
+        const double vp = v_pref - 1e-3;
         if (speed > vp) { pvx = dvx / speed * vp; pvy = dvy / speed * vp; } else { pvx = dvx; pvy = dvy; }
     } else {
         if (speed > 1) { pvx = dvx / speed; pvy = dvy / speed; } else { pvx = dvx; pvy = dvy; }
@@ -1164,7 +1166,7 @@ __device__ int orca_predict_thread_fast(const CrowdParams &P, const Tile &T, flo
 #pragma unroll
         for (int j = c + 1; j < FAST_MAXO; ++j)
             tie = tie || ((((inmask >> c) & (inmask >> j)) & 1u) && dsq[j] == dsq[c]);
-    if (tie && n_others + 1 > 10) { orca_predict_thread(P, T, e, i, genv, out_vx, out_vy); return -1; }
+    if (tie && n_others + 1 > 10) { orca_predict_thread(P, T, e, i, genv, T.gx[k], T.gy[k], T.vpref[k], out_vx, out_vy); return -1; }
     const int n_in = __popc(inmask);
     const int n_nb = n_in < maxNeighbors ? n_in : maxNeighbors;
     int rk[FAST_MAXO];
@@ -1189,6 +1191,97 @@ __device__ int orca_predict_thread_fast(const CrowdParams &P, const Tile &T, flo
         lines.set(r, agent_orca_line(px, py, vx, vy, radius, (float)a, (float)b, (float)cc, (float)d,
                                      (float)(rr + 0.01 + cfg.safety_space), 1.0f / timeHorizon, timeStep));
         if (P.nbr) P.nbr[(size_t)(genv * H + i) * maxNeighbors + r] = id;
+    }
+    if (P.nbr) for (int r = n_nb; r < maxNeighbors; ++r) P.nbr[(size_t)(genv * H + i) * maxNeighbors + r] = -1;
+
+    float rx, ry;
+    const int lineFail = lp2_serial(lines, n_nb, maxSpeed, prefx, prefy, false, rx, ry);
+    out_vx = rx; out_vy = ry;
+    out_n = n_nb; out_speed = maxSpeed;
+    return lineFail < n_nb ? lineFail : -1;
+}
+
+// ORCA up to linearProgram2 for the warp-owns-environments kernel: the same float operations as orca_predict_thread_fast, fed from a
+// float copy of the warp's agents (fs = px, py, vx, vy; fr = radius + 0.01 + safety_space, each narrowed once by its owner instead of
+// once per observer).  Neighbour order: rank = number of candidates that sort before (distSq, then candidate index), counted once per
+// unordered pair; candidates outside neighborDist carry distinct negative keys, so they sort first (their count is subtracted) and
+// never compare equal.  The half-planes are then built in candidate order and stored at their rank -- no search for "the r-th
+// nearest".  Returns lineFail (linearProgram3 still to run), -1 (velocity final) or -2 (exact distance tie in a simulator of more
+// than 10 agents: RVO2's kd-tree visit order decides, the caller runs the general function).
+__device__ int orca_predict_wo(const CrowdParams &P, const float4 *fs, const float *fr, int self, int ebase, int robot_idx, int i, int genv,
+                               double dvx, double dvy, double v_pref, float4 *s_lines, float &out_vx, float &out_vy, int &out_n, float &out_speed)
+{
+    const SnbPolicyCfg &cfg = P.cfg;
+    const int H = P.st.H;
+    const int n_others = H - 1 + P.st.n_obs_extras;
+    const float4 me = fs[self];
+    const float px = me.x, py = me.y, vx = me.z, vy = me.w;
+    const float radius = fr[self];
+    const float maxSpeed = (float)v_pref;
+    const float neighborDist = (float)cfg.neighbor_dist;
+    const float timeHorizon = (float)cfg.time_horizon;
+    const float timeStep = (float)cfg.time_step;
+    const int maxNeighbors = cfg.max_neighbors;
+
+    const double speed = sqrt(fma(dvy, dvy, dvx * dvx));
+    double pvx, pvy;
+    if (cfg.policy == SNB_POLICY_ORCA_PLUS) {
+        const double vp = v_pref - 1e-3;
+        if (speed > vp) { pvx = dvx / speed * vp; pvy = dvy / speed * vp; } else { pvx = dvx; pvy = dvy; }
+    } else {
+        if (speed > 1) { pvx = dvx / speed; pvy = dvy / speed; } else { pvx = dvx; pvy = dvy; }
+    }
+    const float prefx = (float)pvx, prefy = (float)pvy;
+
+    float dsq[FAST_MAXO];
+    int n_in = 0;
+    const float nd2 = neighborDist * neighborDist;
+#pragma unroll
+    for (int c = 0; c < FAST_MAXO; ++c) {
+        float d = -(float)(c + 1);
+        if (c < n_others) {
+            const int idx = (c < H - 1) ? ebase + ((c < i) ? c : c + 1) : robot_idx;
+            const float4 o = fs[idx];
+            const float ddx = px - o.x, ddy = py - o.y;
+            const float v = dot2(ddx, ddy, ddx, ddy);
+            if (maxNeighbors > 0 && v < nd2) { d = v; ++n_in; }
+        }
+        dsq[c] = d;
+    }
+    int rank[FAST_MAXO];
+#pragma unroll
+    for (int c = 0; c < FAST_MAXO; ++c) rank[c] = 0;
+    bool tie = false;
+#pragma unroll
+    for (int c = 1; c < FAST_MAXO; ++c)
+#pragma unroll
+        for (int j = 0; j < c; ++j) {
+            const bool le = dsq[j] <= dsq[c];
+            rank[c] += le ? 1 : 0;
+            rank[j] += le ? 0 : 1;
+            tie = tie || (dsq[j] == dsq[c]);
+        }
+    if (tie && n_others + 1 > 10) return -2;
+    const int n_excl = FAST_MAXO - n_in;
+    unsigned long long packed = 0ull;                       // 4 bits per candidate: its rank among the neighbours, 15 = not one
+#pragma unroll
+    for (int c = 0; c < FAST_MAXO; ++c)
+        packed |= (unsigned long long)(dsq[c] >= 0.0f ? (unsigned)(rank[c] - n_excl) : 15u) << (4 * c);
+    const int n_nb = n_in < maxNeighbors ? n_in : maxNeighbors;
+    if (P.nbr_cnt) P.nbr_cnt[genv * H + i] = n_nb;
+
+    const SmemLinesT<32> lines{s_lines};
+    const float invTH = 1.0f / timeHorizon;
+    for (int c = 0; c < n_others; ++c) {
+        const int r = (int)((unsigned)(packed >> (4 * c)) & 15u);
+        if (r < n_nb) {
+            const bool human = c < H - 1;
+            const int j = human ? ((c < i) ? c : c + 1) : H;
+            const int idx = human ? ebase + j : robot_idx;
+            const float4 o = fs[idx];
+            lines.set(r, agent_orca_line(px, py, vx, vy, radius, o.x, o.y, o.z, o.w, fr[idx], invTH, timeStep));
+            if (P.nbr) P.nbr[(size_t)(genv * H + i) * maxNeighbors + r] = j;
+        }
     }
     if (P.nbr) for (int r = n_nb; r < maxNeighbors; ++r) P.nbr[(size_t)(genv * H + i) * maxNeighbors + r] = -1;
 
@@ -1572,7 +1665,7 @@ __global__ void __launch_bounds__(CROWD_THREADS, 3) crowd_step_kernel(const Crow
                         const int slot = atomicAdd(s_lp3_count, 1);
                         s_lp3[slot] = make_int4(threadIdx.x | (task << 16), n_l | (fail << 8), __float_as_int(spd), 0);
                     }
-                } else orca_predict_thread(P, T, e, i, genv, fx, fy);
+                } else orca_predict_thread(P, T, e, i, genv, T.gx[e * H + i], T.gy[e * H + i], T.vpref[e * H + i], fx, fy);
                 ax = (double)fx; ay = (double)fy;
             }
             T.act[2 * task] = ax; T.act[2 * task + 1] = ay;
@@ -1748,9 +1841,15 @@ __global__ void __launch_bounds__(CROWD_THREADS, 3) crowd_step_kernel(const Crow
 // of the small-launch path).  Same float operations per human as everywhere else => bit-identical results.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int FW_WARPS = 4;
-static __host__ __device__ inline size_t fw_warp_bytes(int line_cap)
+// per-warp shared memory: half-planes [line_cap][32] float4 (the next positions of phase 2 reuse their first 512 bytes), 32 float4 of
+// LP3 scratch, the float copy of the warp's humans and robots (fs, fr), and the fp64 state the step itself needs (5 x 32 humans,
+// 5 x robots).  7.6 KB per warp at H = 10, max_neighbors = 10 -> 7 CTAs of 4 warps per SM.
+static __host__ __device__ inline int fw_exn(int H, int E) { return ((32 / H) * E + 1) & ~1; }
+static __host__ __device__ inline size_t fw_warp_bytes(int line_cap, int H, int E)
 {
-    return (size_t)(13 * 32 + 64) * sizeof(double) + (size_t)line_cap * 32 * sizeof(float4) + 32 * sizeof(Line);
+    const int fsn = 32 + fw_exn(H, E);
+    return (size_t)line_cap * 32 * sizeof(float4) + 32 * sizeof(float4) + (size_t)fsn * sizeof(float4) + (((size_t)fsn * sizeof(float) + 15) & ~(size_t)15) +
+           (size_t)(5 * 32 + 5 * fw_exn(H, E)) * sizeof(double);
 }
 
 __global__ void __launch_bounds__(32 * FW_WARPS) crowd_orca_warp_kernel(const CrowdParams P)
@@ -1762,15 +1861,19 @@ __global__ void __launch_bounds__(32 * FW_WARPS) crowd_orca_warp_kernel(const Cr
     const int env0 = (blockIdx.x * FW_WARPS + w) * epw;
     const int nenv = min(epw, P.st.B - env0);
     if (nenv <= 0) return;                                  // the whole warp leaves together; nobody waits for it
-    double *sd = reinterpret_cast<double *>(fw_smem + (size_t)w * fw_warp_bytes(P.fast_lines));
+    const int exn = fw_exn(H, E), fsn = 32 + exn;
+    unsigned char *wb = fw_smem + (size_t)w * fw_warp_bytes(P.fast_lines, H, E);
+    float4 *s_lines = reinterpret_cast<float4 *>(wb); wb += (size_t)P.fast_lines * 32 * sizeof(float4);
+    float4 *scratch = reinterpret_cast<float4 *>(wb); wb += 32 * sizeof(float4);
+    float4 *fs = reinterpret_cast<float4 *>(wb); wb += (size_t)fsn * sizeof(float4);
+    float *fr = reinterpret_cast<float *>(wb); wb += ((size_t)fsn * sizeof(float) + 15) & ~(size_t)15;
+    double *sd = reinterpret_cast<double *>(wb);
     Tile T;
-    T.px = sd; sd += 32; T.py = sd; sd += 32; T.vx = sd; sd += 32; T.vy = sd; sd += 32;
-    T.rad = sd; sd += 32; T.gx = sd; sd += 32; T.gy = sd; sd += 32; T.vpref = sd; sd += 32;
-    T.ex_px = sd; sd += 32; T.ex_py = sd; sd += 32; T.ex_vx = sd; sd += 32; T.ex_vy = sd; sd += 32; T.ex_rad = sd; sd += 32;
+    T.px = sd; sd += 32; T.py = sd; sd += 32; T.vx = sd; sd += 32; T.vy = sd; sd += 32; T.rad = sd; sd += 32;
+    T.ex_px = sd; sd += exn; T.ex_py = sd; sd += exn; T.ex_vx = sd; sd += exn; T.ex_vy = sd; sd += exn; T.ex_rad = sd; sd += exn;
+    T.gx = T.gy = T.vpref = nullptr;                        // goal and v_pref stay in their owner's registers
     T.act = nullptr; T.segs = nullptr;
-    double *s_next = sd; sd += 64;
-    float4 *s_lines = reinterpret_cast<float4 *>(sd);
-    Line *scratch = reinterpret_cast<Line *>(s_lines + (size_t)P.fast_lines * 32);
+    double *s_next = reinterpret_cast<double *>(s_lines);   // phase 2 only: the half-planes are dead by then
 
     const int nA = nenv * H;
     const bool live = lane < nA;
@@ -1778,21 +1881,32 @@ __global__ void __launch_bounds__(32 * FW_WARPS) crowd_orca_warp_kernel(const Cr
     const int genv = env0 + e;
     const size_t g = (size_t)env0 * H + lane;
     const bool on = live && !(P.active && !P.active[genv]);
+    const double rad_pad = 0.01 + P.cfg.safety_space;
+    double my_px = 0.0, my_py = 0.0, my_gx = 0.0, my_gy = 0.0, my_vpref = 0.0, my_rad = 0.0;
     if (live) {
-        T.px[lane] = P.st.px[g]; T.py[lane] = P.st.py[g]; T.vx[lane] = P.st.vx[g]; T.vy[lane] = P.st.vy[g];
-        T.rad[lane] = P.st.radius[g]; T.gx[lane] = P.st.gx[g]; T.gy[lane] = P.st.gy[g]; T.vpref[lane] = P.st.vpref[g];
+        my_px = P.st.px[g]; my_py = P.st.py[g];
+        const double vx = P.st.vx[g], vy = P.st.vy[g];
+        my_rad = P.st.radius[g]; my_gx = P.st.gx[g]; my_gy = P.st.gy[g]; my_vpref = P.st.vpref[g];
+        T.px[lane] = my_px; T.py[lane] = my_py; T.vx[lane] = vx; T.vy[lane] = vy; T.rad[lane] = my_rad;
+        fs[lane] = make_float4((float)my_px, (float)my_py, (float)vx, (float)vy);
+        fr[lane] = (float)(my_rad + rad_pad);
     }
     if (lane < nenv * E) {
         const size_t x = (size_t)env0 * E + lane;
-        T.ex_px[lane] = P.st.ex_px[x]; T.ex_py[lane] = P.st.ex_py[x]; T.ex_vx[lane] = P.st.ex_vx[x]; T.ex_vy[lane] = P.st.ex_vy[x];
-        T.ex_rad[lane] = P.st.ex_radius[x];
+        const double a = P.st.ex_px[x], b = P.st.ex_py[x], c = P.st.ex_vx[x], d = P.st.ex_vy[x], r = P.st.ex_radius[x];
+        T.ex_px[lane] = a; T.ex_py[lane] = b; T.ex_vx[lane] = c; T.ex_vy[lane] = d; T.ex_rad[lane] = r;
+        fs[32 + lane] = make_float4((float)a, (float)b, (float)c, (float)d);
+        fr[32 + lane] = (float)(r + rad_pad);
     }
     __syncwarp();
 
     // ---- phase 1: ORCA per lane up to linearProgram2; linearProgram3 warp-cooperatively, one human at a time ----
     float fx = 0.0f, fy = 0.0f, spd = 0.0f;
     int fail = -1, n_l = 0;
-    if (on) fail = orca_predict_thread_fast<32>(P, T, s_lines + lane, e, i, genv, fx, fy, n_l, spd);
+    if (on) {
+        fail = orca_predict_wo(P, fs, fr, lane, e * H, 32 + e * E, i, genv, my_gx - my_px, my_gy - my_py, my_vpref, s_lines + lane, fx, fy, n_l, spd);
+        if (fail == -2) { orca_predict_thread(P, T, e, i, genv, my_gx, my_gy, my_vpref, fx, fy); fail = -1; }
+    }
     unsigned need = __ballot_sync(FULL, fail >= 0);
     while (need) {
         const int src = __ffs(need) - 1;
@@ -1803,9 +1917,9 @@ __global__ void __launch_bounds__(32 * FW_WARPS) crowd_orca_warp_kernel(const Cr
         if (P.lp3_mode == 0) {
             Line my; my.px = 0.f; my.py = 0.f; my.dx = 1.f; my.dy = 0.f;
             if (lane < n) my = SmemLinesT<32>{s_lines + src}[lane];
-            lp3_warp(my, n, 0, begin, r, rx, ry, lane, scratch);
+            lp3_warp(my, n, 0, begin, r, rx, ry, lane, reinterpret_cast<Line *>(scratch));
         } else {
-            lp3_warp_skip(s_lines + src, n, begin, r, rx, ry, lane, reinterpret_cast<float4 *>(scratch));
+            lp3_warp_skip(s_lines + src, n, begin, r, rx, ry, lane, scratch);
         }
         if (lane == src) { fx = rx; fy = ry; }
     }
@@ -1818,7 +1932,8 @@ __global__ void __launch_bounds__(32 * FW_WARPS) crowd_orca_warp_kernel(const Cr
     // ---- phase 2a: no wall segments -> the action is not clamped; next position (Agent.compute_position) ----
     const double dt = P.cfg.time_step;
     double nx = 0.0, ny = 0.0;
-    if (on) { nx = T.px[lane] + c0 * dt; ny = T.py[lane] + c1 * dt; s_next[2 * lane] = nx; s_next[2 * lane + 1] = ny; }
+    __syncwarp();                                           // every lane is done with the half-planes s_next overlays
+    if (on) { nx = my_px + c0 * dt; ny = my_py + c1 * dt; s_next[2 * lane] = nx; s_next[2 * lane + 1] = ny; }
     __syncwarp();
 
     // ---- phase 2b: lane e < nenv is the robot of environment e (crowd_sim_plus.py:1058-1172, same expressions as crowd_step_kernel) ----
@@ -1890,12 +2005,12 @@ __global__ void __launch_bounds__(32 * FW_WARPS) crowd_orca_warp_kernel(const Cr
     if (on) {
         P.st.px[g] = nx; P.st.py[g] = ny; P.st.vx[g] = c0; P.st.vy[g] = c1;
         P.st.theta[g] = atan2(c1, c0);
-        double ggx = T.gx[lane], ggy = T.gy[lane];
+        double ggx = my_gx, ggy = my_gy;
         if (P.door.enabled) {
             get_g_xy(P.door, nx, ny, P.st.fgx[g], P.st.fgy[g], ggx, ggy);
             P.st.gx[g] = ggx; P.st.gy[g] = ggy;
         }
-        if (P.st.human_time[g] == 0 && npnorm2(nx - ggx, ny - ggy) < T.rad[lane]) P.st.human_time[g] = gt_new;
+        if (P.st.human_time[g] == 0 && npnorm2(nx - ggx, ny - ggy) < my_rad) P.st.human_time[g] = gt_new;
     }
 }
 
@@ -1991,7 +2106,7 @@ static int launch_crowd(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const S
     // the barrier-free kernel: plain ORCA, no walls, the simulator's single robot, update / policy-only (not the what-if look-ahead)
     if (P.fast_lines && P.n_seg == 0 && st->E == 1 && full_step != 2 && st->H <= 32 && !getenv("SNB_CROWD_NO_WARPOWN")) {
         const int epw = 32 / st->H;
-        const size_t wsm = fw_warp_bytes(P.fast_lines) * FW_WARPS;
+        const size_t wsm = fw_warp_bytes(P.fast_lines, st->H, st->E) * FW_WARPS;
         static std::once_flag once_w;
         static cudaError_t attr_w = cudaSuccess;
         std::call_once(once_w, [] { attr_w = cudaFuncSetAttribute(crowd_orca_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); });

@@ -31,3 +31,14 @@ for k in range(steps):
     ts.append(a.elapsed_time(b))
 t = float(np.mean(ts[2:]))
 print(f"ORCA {B} x 10: {t * 1e3:.1f} us per step, {B / (t * 1e-3) / 1e6:.1f} M env-steps/s  (all: {[round(x, 3) for x in ts]})")
+if len(sys.argv) > 3:      # a whole episode, every launch timed
+    env.reset('test', test_cases=np.arange(B) % 500)
+    ep = []
+    for k in range(int(sys.argv[3])):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); env._launch(act, None); b.record(); torch.cuda.synchronize()
+        ep.append(a.elapsed_time(b))
+    ep = np.asarray(ep)
+    print(f"episode of {len(ep)} steps: mean {ep.mean() * 1e3:.1f} us = {B / (ep.mean() * 1e-3) / 1e6:.1f} M env-steps/s; min {ep.min():.3f} max {ep.max():.3f} ms at step {ep.argmax()}; "
+          f"by decade {[round(float(ep[k:k + 10].mean()), 2) for k in range(0, len(ep), 10)]}")
