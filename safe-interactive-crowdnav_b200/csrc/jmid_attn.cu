@@ -388,6 +388,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     tc::named_bar_sync(1 + t, 128);
                 }
                 store(s0, 0, 0);
+#if !defined(SNB_ATTN_NO_LAG) && SNB_ATTN_LAG_AT == 0
+                if (t == 0 && j == 0 && has_b) tc::mbar_arrive(lag);
+#endif
                 exp_pack(s1); store(s1, 0, 4);
 #if !defined(SNB_ATTN_NO_LAG) && SNB_ATTN_LAG_AT == 1
                 if (t == 0 && j == 0 && has_b) tc::mbar_arrive(lag);
