@@ -166,3 +166,44 @@ def test_configure_refuses_what_it_does_not_implement():
     assert env.human_policy.is_bottleneck is True
     env.reset('val', test_cases=[0, 1, 2, 3])                        # another layout with the SAME policy object
     assert env.human_policy.is_bottleneck is False
+
+
+def test_orca_hbm_sized_batch_replicas_stay_bit_identical_and_match_the_oracle():
+    """BASELINE-scale property (size independent): 2^18 environments cycle through 512 distinct test cases, so environment b and
+    b mod 512 start from the same scene but sit on different lanes, warps and CTAs of the warp-owns-environments kernel.  After 24 steps
+    through the congested middle of the crossing (where a third of the humans need linearProgram3) every replica must hold the SAME bits,
+    and the first 512 must hold the bits of the CPU oracle stepping those scenes from the same post-reset state."""
+    import oracle_lib as ol
+    from snb import rollout
+    B, H, R, steps = 1 << 18, 10, 512, 24
+    env = _env(B, H, 30)
+    env.freeze_done = False
+    env.reset('test', test_cases=np.arange(B) % R)
+    robot = rollout.LinearRobot(env)
+    st = env.state
+    for n in ("px", "py", "vx", "vy", "gx", "gy", "vpref"):
+        a = getattr(st, n).view(B // R, R, H)
+        assert torch.equal(a, a[0:1].expand_as(a)), n        # the device reset is replica-invariant too
+    # the oracle starts from the device's post-reset state of the first R environments (the generators agree to libm ulps only)
+    oenv, pcfg, dcfg, rcfg = RO.reset(list(range(R)), H, time_limit=30.0, starts_moving=0, reward=dict(collision_penalty=-0.25, freezing_penalty=-0.125))
+    for n in ("px", "py", "vx", "vy", "theta", "gx", "gy", "fgx", "fgy", "vpref", "radius", "human_time"):
+        getattr(oenv, n)[:] = getattr(st, n)[:R].cpu().numpy().ravel()
+    for n, m in (("rpx", "ex_px"), ("rpy", "ex_py"), ("rvx", "ex_vx"), ("rvy", "ex_vy")):
+        getattr(oenv, n)[:] = getattr(st, m)[:R].cpu().numpy().ravel()
+    for n in ("rtheta", "rgx", "rgy", "global_time", "prev_dist"):
+        getattr(oenv, n)[:] = getattr(st, n)[:R].cpu().numpy().ravel()
+    for k in range(steps):
+        act = robot.act()
+        a_host = act[:R].cpu().numpy().copy()
+        env.step(act)
+        ol.env_step(pcfg, dcfg, rcfg, oenv, a_host, n_threads=8)
+    torch.cuda.synchronize()
+    env.check_status()
+    for n in ("px", "py", "vx", "vy", "theta", "human_time"):
+        a = getattr(st, n).view(B // R, R, H)
+        assert torch.equal(a, a[0:1].expand_as(a)), n
+    fl = env.flags.view(B // R, R)
+    assert torch.equal(fl, fl[0:1].expand_as(fl))
+    for n in ("px", "py", "vx", "vy"):
+        got = getattr(st, n)[:R].cpu().numpy().ravel()
+        assert np.array_equal(got, getattr(oenv, n)), (n, np.max(np.abs(got - getattr(oenv, n))))
