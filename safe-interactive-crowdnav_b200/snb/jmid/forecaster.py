@@ -257,13 +257,34 @@ def randn(shape, seed, offset=0, device="cuda"):
     return out
 
 
-class _MidModelFacade:
-    """What callers reach through `forecaster.mid_model` / `.model` in the reference (mid.py:73-104): `num_samples`, `config`."""
+class _AutoEncoderFacade:
+    """`MID.model` (models/autoencoder.py): only the member inference callers reach, `.diffusion`."""
 
-    def __init__(self, cfg, drawn):
+    def __init__(self, diffusion):
+        self.diffusion = diffusion
+
+
+class _MidModelFacade:
+    """What callers reach through `forecaster.mid_model` / `.model` in the reference (mid.py:73-104): `num_samples`, `config`, and
+    `model.diffusion.sample_sicnav_inference(...)` (models/diffusion.py:478) bound to the CUDA denoiser (built on first use)."""
+
+    def __init__(self, cfg, drawn, ddpm=None, joint=True, max_agents=10, device="cuda"):
         self.config = type("MidConfig", (dict,), {"__getattr__": lambda s_, k: s_[k]})(cfg)
         self.num_samples = drawn
         self.sicnav_inference = True
+        self._ddpm, self._joint, self._max_agents, self._device = ddpm, joint, max_agents, device
+        self._ae = None
+
+    @property
+    def model(self):
+        if self._ae is None:
+            from .diffusion import DiffusionTraj
+            self._ae = _AutoEncoderFacade(DiffusionTraj(self._ddpm, joint=self._joint, max_agents=self._max_agents, device=self._device))
+        return self._ae
+
+    def eval(self, env=None, *a, **k):
+        raise _capi.SnbError("snb predictor: MID.eval(Environment) has no counterpart (scenes are built on the device); "
+                             "call HumanTrajectoryForecasterSim.predict() or mid_model.model.diffusion.sample_sicnav_inference(...)")
 
 
 class HumanTrajectoryForecasterSim:
@@ -274,8 +295,9 @@ class HumanTrajectoryForecasterSim:
     [sim] human_num (mid_sim_wrapper.py:171-195).  mid_config_file: yaml path, mapping or attribute object with `model_path`,
     `diffnet` (JointPredictionTransformerConcatLinear = JMID, TransformerConcatLinear = iMID), `num_samples` (drawn), `step_size`,
     `sampling` (test_time_configs/mid_jp.yaml).  `weights=(encoder, ddpm)` bypasses the checkpoint file (tests).
-    Restrictions, stated: past_num_frames must be 6 (the shipped value) and the history frames must be time_step apart, so the
-    reference's resampling / interpolation (mid_sim_wrapper.py:283-310) is the identity; sampling must be "ddim"."""
+    The history join / resampling / interpolation of mid_sim_wrapper.py:244-298 is applied (snb/jmid/history.py; the identity in the
+    simulator).  Restrictions, stated: past_num_frames must be 6 (the shipped value) and 6 frames must be left after resampling;
+    sampling must be "ddim"."""
 
     def __init__(self, env_config=None, mid_config_file=None, weights=None, device="cuda", seed=0):
         if env_config is None:
@@ -304,7 +326,7 @@ class HumanTrajectoryForecasterSim:
         self.batch = ForecasterBatch(enc, ddpm, max_envs=1, H=self.num_hums, num_samples=drawn,
                                      num_ret=min(self.num_ret_samples, drawn), step_size=int(cfg.get("step_size", 20)),
                                      horizon=self.predict_horizon, joint=joint, dt=self.time_step, device=device, seed=seed)
-        self.mid_model = self.model = _MidModelFacade(cfg, drawn)
+        self.mid_model = self.model = _MidModelFacade(cfg, drawn, ddpm, joint, self.num_hums, device)
         self.mid_env = None          # the Trajectron Environment object has no counterpart: scenes are built on the device
         self.prev_states = [[] for _ in range(self.num_hums)]
         self.prev_robot_states = []
@@ -319,18 +341,20 @@ class HumanTrajectoryForecasterSim:
             self.prev_robot_states.pop(0)
 
     def _histories(self):
-        hist = np.asarray(self.prev_states, np.float64)
-        rob = np.asarray(self.prev_robot_states[-self.num_hist_frames:], np.float64)
-        ts = hist[0, :, 2]
-        if not (np.allclose(np.diff(ts), self.time_step, atol=1e-9) and np.allclose(rob[:, 2], ts, atol=1e-9)):
-            raise _capi.SnbError("snb predictor: history frames must be exactly time_step apart (resampling is not implemented)")
-        return hist[None, :, :, :2], rob[None, :, :2]
+        """The joined, resampled frame table of mid_sim_wrapper.py:244-298 (identity when the frames are time_step apart)."""
+        from .history import resample_histories
+        hum, rob = resample_histories(self.prev_states, self.prev_robot_states, self.time_step, self.num_hist_frames)
+        if hum.shape[1] < self.num_hist_frames:
+            raise _capi.SnbError(f"snb predictor: {hum.shape[1]} frames are left after resampling the histories to time_step "
+                                 f"(poses recorded faster than time_step, or stamps missing from an agent); the device pipeline "
+                                 f"needs past_num_frames = {self.num_hist_frames}")
+        return hum[None], rob[None]
 
     def predict_ret_best(self, noise=None):
         """-> (forecasts [H, k, T+1, 2] float64, log-weights [H, k] float64), mid_sim_wrapper.py:482-509."""
-        if len(self.prev_states[0]) < self.num_hist_frames:
-            raise _capi.SnbError("predict_ret_best: fewer than past_num_frames history frames")
-        hist, rob = self._histories()
+        if not self.prev_states[0] or not self.prev_robot_states:
+            raise _capi.SnbError("predict_ret_best: no history frames (call update_state_hists first)")
+        hist, rob = self._histories()          # raises unless past_num_frames frames are left after the reference's resampling
         fc, lw = self.batch.predict_host(hist, rob, None if noise is None else noise[None])
         return fc[0], lw[0]
 

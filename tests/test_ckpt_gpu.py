@@ -197,6 +197,13 @@ def test_reference_literal_constructor_call(tmp_path, monkeypatch):
     assert tuple(top.shape) == (2, 8, 8, 2) and tuple(w.shape) == (2, 8) and abs(float(w[0].exp().sum()) - 1.0) < 1e-4
     flat = pos2.reshape(n_draw, -1)
     assert all(bool((flat == top[:, j].cpu().reshape(1, -1)).all(1).any()) for j in range(8))     # the kept ones are drawn samples
+    # the inner entry the reference's AutoEncoder calls (models/autoencoder.py:33-44 -> diffusion.py:478), through the same object chain:
+    # forecaster.mid_model (MID) .model (AutoEncoder) .diffusion (DiffusionTraj); shipped weights, the reference's x_T and velocities
+    ctx = torch.from_numpy(C4[tag + "_ctx"])
+    traj, nsteps = sim.mid_model.model.diffusion.sample_sicnav_inference(8, ctx.cuda(), n_draw, True, point_dim=2, flexibility=0.0, ret_traj=False,
+                                                                         sampling="ddim", step=step, x_T=torch.from_numpy(C4[tag + "_xT"]))
+    assert tuple(traj.shape) == (n_draw, H, 8, 2) and nsteps == n_draw * (step + 1)
+    assert np.max(np.abs(traj.cpu().numpy() - C4[tag + "_vel"])) <= 2e-2
 
 
 def test_step_size_must_divide_the_diffusion_steps():

@@ -157,3 +157,39 @@ def test_predict_host_equals_device_path():
     pos_d = den.integrate(vel, p0.cuda()).cpu().numpy()
     assert np.array_equal(pos_h, pos_d)
     assert abs(den.flops_per_iter() - (12913152.0 * 96 + 6144.0 * 96 * 96)) < 1.0
+
+
+@pytest.mark.parametrize("joint", [True, False])
+def test_sample_sicnav_inference_has_the_reference_signature_and_values(joint):
+    """snb.jmid.DiffusionTraj.sample_sicnav_inference(num_points, context, sample, bestof, point_dim, flexibility, ret_traj, sampling,
+    step) -- the call of models/autoencoder.py:33-44 -- against the oracle's restatement of diffusion.py:478-541 with the same x_T."""
+    from snb import _capi
+    from snb.jmid import DiffusionTraj
+    w = JO.make_random_weights(int(G["rand_seed"]))
+    d = DiffusionTraj(w, joint=joint, max_agents=4)
+    g = torch.Generator().manual_seed(3)
+    A, S, T = 3, 5, 8
+    ctx = torch.randn(A, 256, generator=g); xT = torch.randn(S * A, T, 2, generator=g)
+    traj, n = d.sample_sicnav_inference(T, ctx.cuda(), S, True, point_dim=2, flexibility=0.0, ret_traj=False, sampling="ddim", step=20, x_T=xT)
+    assert tuple(traj.shape) == (S, A, T, 2) and traj.is_cuda and n == S * 21          # diffusion.py:539-541
+    with torch.no_grad():
+        ref = JO.sample(w, ctx, xT, step=20, joint=joint)
+    assert (traj.cpu() - ref).abs().max().item() <= 3e-2
+    # step = 40 -> stride int(100 / 40) = 2 -> 50 iterations, like the reference; a host context comes back on the host
+    traj40, n40 = d.sample_sicnav_inference(T, ctx, S, True, sampling="ddim", step=40, x_T=xT)
+    assert not traj40.is_cuda and n40 == S * 51
+    with torch.no_grad():
+        ref40 = JO.sample(w, ctx, xT, step=40, joint=joint)
+    assert (traj40 - ref40).abs().max().item() <= 3e-2
+    # bestof = False starts from zeros (diffusion.py:503-506): deterministic
+    z1, _ = d.sample_sicnav_inference(T, ctx.cuda(), S, False, sampling="ddim", step=20)
+    with torch.no_grad():
+        refz = JO.sample(w, ctx, torch.zeros(S * A, T, 2), step=20, joint=joint)
+    assert (z1.cpu() - refz).abs().max().item() <= 3e-2
+    # bestof = True draws: two calls differ
+    r1, _ = d.sample_sicnav_inference(T, ctx.cuda(), S, True, sampling="ddim", step=20)
+    r2, _ = d.sample_sicnav_inference(T, ctx.cuda(), S, True, sampling="ddim", step=20)
+    assert not torch.equal(r1, r2)
+    for bad in (dict(sampling="ddpm", step=20), dict(sampling="ddim", step=30), dict(sampling="ddim", step=20, ret_traj=True)):
+        with pytest.raises(_capi.SnbError):
+            d.sample_sicnav_inference(T, ctx.cuda(), S, True, **bad)

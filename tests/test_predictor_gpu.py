@@ -300,6 +300,46 @@ def test_drop_in_forecaster_sim_class():
     assert np.array_equal(lw, G[tag + "_logw"])
 
 
+def test_forecaster_sim_resamples_sparse_histories_like_the_reference():
+    """Poses pushed every 0.5 s into a 0.25 s predictor: the reference's resample + linear interpolation (mid_sim_wrapper.py:283-298)
+    fills the empty windows, so the forecasts must equal those of a second object fed the interpolated frames one time_step apart."""
+    from snb.jmid.forecaster import HumanTrajectoryForecasterSim
+    H, n_draw = 4, 6
+    cfg = configparser.RawConfigParser()
+    cfg.read_dict({"env": {"time_step": "0.25"}, "sim": {"human_num": str(H)},
+                   "human_trajectory_forecaster": {"past_num_frames": "6", "prediction_horizon": "8", "num_samples": str(n_draw)}})
+    w = (enc_weights("rand"), JO.make_random_weights(int(G["ddpm_seed"])))
+    mk = lambda: HumanTrajectoryForecasterSim(cfg, {"num_samples": n_draw, "step_size": 5, "joint_prediction": True}, weights=w)
+    sparse, dense = mk(), mk()
+
+    class St:
+        def __init__(self, p):
+            self.position = (float(p[0]), float(p[1]))
+    rng = np.random.default_rng(8)
+    p0 = rng.uniform(-1.5, 1.5, (H + 1, 2)); v = rng.uniform(-0.6, 0.6, (H + 1, 2)); acc = rng.uniform(-0.3, 0.3, (H + 1, 2))
+    pose = lambda t: p0 + v * t + 0.5 * acc * t * t                     # curved paths: interpolated frames differ from the true ones
+    ts_sparse = [0.0, 0.5, 1.0, 1.5]                                      # -> windows 0, .25, ..., 1.5: 7 rows, the newest 6 are kept
+    for t in ts_sparse:
+        P = pose(t)
+        sparse.update_state_hists(St(P[H]), [St(P[i]) for i in range(H)], t)
+    for t in np.arange(0.25, 1.5 + 1e-9, 0.25):
+        k = int(t // 0.5)
+        P = pose(t) if abs(t - 0.5 * round(t / 0.5)) < 1e-12 else pose(0.5 * k) + (pose(0.5 * (k + 1)) - pose(0.5 * k)) * 0.5
+        dense.update_state_hists(St(P[H]), [St(P[i]) for i in range(H)], float(t))
+    nz = np.random.default_rng(9).standard_normal((n_draw, H, 8, 2)).astype(np.float32)
+    f1, l1 = sparse.predict_ret_best(noise=nz)
+    f2, l2 = dense.predict_ret_best(noise=nz)
+    assert np.array_equal(f1, f2) and np.array_equal(l1, l2)
+    # poses recorded faster than time_step leave fewer than 6 windows in the six retained raw entries (the reference's quirk): refused loudly
+    fast = mk()
+    for k in range(8):
+        P = pose(0.05 * k)
+        fast.update_state_hists(St(P[H]), [St(P[i]) for i in range(H)], 0.05 * k)
+    from snb import _capi
+    with pytest.raises(_capi.SnbError, match="after resampling"):
+        fast.predict_ret_best(noise=nz)
+
+
 IG = np.load(f"{GOLDEN}/ingest_cases.npz")
 
 
