@@ -43,8 +43,100 @@ template <int BN> struct GemmCfg {
 struct RowFold {
     float rstd, nmr;       // FOLD: the A operand was z, not LN(z):  v = rstd * acc - rstd * mu * colsum[n] + bias'[n];  nmr = -rstd * mu
     float r_rstd, r_mu;    // RES == 2: the residual is LN(z_res) recomputed from z_res and its row statistics
-    float sum, sumsq;      // RES != 0: statistics of the (bf16-rounded) row this thread writes, for the next consumer
+    uint64_t sum2, sq2;    // RES != 0: sum / sum of squares of the row this thread writes, two interleaved partial sums each (FADD2 / FFMA2)
 };
+
+// Packed-pair (f32x2) forms of the fold epilogue: one FFMA2 / FADD2 per TWO accumulator columns.  The drain of an out-proj tile
+// (K = 512: 2048 clk of MMAs per tile) spent ~2500 issue slots per scheduler on scalar epilogue arithmetic and was the limiter of
+// the RES kernels (ncu: neither DRAM nor the tensor pipe above 55 %); packed it is about half of that.
+template <int EPI, bool FOLD>
+__device__ __forceinline__ void epilogue_math2(const uint32_t (&acc)[32], uint64_t (&v2)[16], const float *s_bias, const GemmEpi &ep,
+                                               int col0_global, int ba, const RowFold &rf)
+{
+    const ulonglong2 *b2 = reinterpret_cast<const ulonglong2 *>(s_bias);
+    if constexpr (FOLD) {
+        const ulonglong2 *c2 = reinterpret_cast<const ulonglong2 *>(ep.colsum + col0_global);
+        const uint64_t rstd2 = tc::f2_pack(rf.rstd, rf.rstd), nmr2 = tc::f2_pack(rf.nmr, rf.nmr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const ulonglong2 b = b2[j], c = __ldg(c2 + j);
+            v2[2 * j] = tc::f2_fma(tc::f2_pack(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1])), rstd2, tc::f2_fma(nmr2, c.x, b.x));
+            v2[2 * j + 1] = tc::f2_fma(tc::f2_pack(__uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3])), rstd2, tc::f2_fma(nmr2, c.y, b.y));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const ulonglong2 b = b2[j];
+            v2[2 * j] = tc::f2_add(tc::f2_pack(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1])), b.x);
+            v2[2 * j + 1] = tc::f2_add(tc::f2_pack(__uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3])), b.y);
+        }
+    }
+    if constexpr (EPI == EPI_BIAS_RELU_BF16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float lo, hi;
+            tc::f2_unpack(v2[j], lo, hi);
+            v2[j] = tc::f2_pack(fmaxf(lo, 0.0f), fmaxf(hi, 0.0f));
+        }
+    }
+    if constexpr (EPI == EPI_CSL_BF16) {
+        const ulonglong2 *g2 = reinterpret_cast<const ulonglong2 *>(ep.gate + (size_t)ba * ep.tab_ld + col0_global);
+        const ulonglong2 *h2 = reinterpret_cast<const ulonglong2 *>(ep.hbias + (size_t)ba * ep.tab_ld + col0_global);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const ulonglong2 g = __ldg(g2 + j), h = __ldg(h2 + j);
+            v2[2 * j] = tc::f2_fma(v2[2 * j], g.x, h.x);
+            v2[2 * j + 1] = tc::f2_fma(v2[2 * j + 1], g.y, h.y);
+        }
+    }
+}
+
+// + residual for one 32-column chunk (`rz` = the thread's 32 residual bf16 of these columns), row statistics, bf16 pairs in pk[16].
+// RES == 2: the residual is LayerNorm(z_res) = gamma (z rr + rn) + beta with rr = rstd, rn = -mu rstd of the residual's row; beta was
+// added to the bias slice in shared memory when the tile started, so a pair costs two FFMA2.  The statistics are those of the ROUNDED
+// values (what the consuming GEMM reads); taking them before rounding (-DSNB_STATS_UNROUNDED) saves two integer ops per pair, is not
+// faster in the step and costs parity with the shipped checkpoint (eps 2.1e-2 instead of 1.9e-2).
+template <int RES>
+__device__ __forceinline__ void residual_pack2(uint64_t (&v2)[16], const uint4 (&rz)[4], const GemmEpi &ep, int col0_global, RowFold &rf,
+                                               uint32_t (&pk)[16])
+{
+    if constexpr (RES != 0) {
+        const uint32_t w[16] = {rz[0].x, rz[0].y, rz[0].z, rz[0].w, rz[1].x, rz[1].y, rz[1].z, rz[1].w,
+                                rz[2].x, rz[2].y, rz[2].z, rz[2].w, rz[3].x, rz[3].y, rz[3].z, rz[3].w};
+        if constexpr (RES == 2) {
+            const ulonglong2 *g2 = reinterpret_cast<const ulonglong2 *>(ep.res_gamma + col0_global);
+            const float rn = -rf.r_mu * rf.r_rstd;
+            const uint64_t rr2 = tc::f2_pack(rf.r_rstd, rf.r_rstd), rn2 = tc::f2_pack(rn, rn);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const ulonglong2 g = __ldg(g2 + j);
+                const uint64_t za = tc::f2_pack(__uint_as_float(w[2 * j] << 16), __uint_as_float(w[2 * j] & 0xffff0000u));
+                const uint64_t zb = tc::f2_pack(__uint_as_float(w[2 * j + 1] << 16), __uint_as_float(w[2 * j + 1] & 0xffff0000u));
+                v2[2 * j] = tc::f2_fma(g.x, tc::f2_fma(za, rr2, rn2), v2[2 * j]);
+                v2[2 * j + 1] = tc::f2_fma(g.y, tc::f2_fma(zb, rr2, rn2), v2[2 * j + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                v2[j] = tc::f2_add(v2[j], tc::f2_pack(__uint_as_float(w[j] << 16), __uint_as_float(w[j] & 0xffff0000u)));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        float lo, hi;
+        tc::f2_unpack(v2[j], lo, hi);
+        pk[j] = tc::pack_bf16(lo, hi);
+        if constexpr (RES != 0) {
+#ifdef SNB_STATS_UNROUNDED
+            const uint64_t x2 = v2[j];
+#else
+            const uint64_t x2 = tc::f2_pack(__uint_as_float(pk[j] << 16), __uint_as_float(pk[j] & 0xffff0000u));   // what the consumer will read
+#endif
+            rf.sum2 = tc::f2_add(rf.sum2, x2);
+            rf.sq2 = tc::f2_fma(x2, x2, rf.sq2);
+        }
+    }
+}
 
 template <int EPI, bool FOLD = false>
 __device__ __forceinline__ void epilogue_math(const uint32_t (&acc)[32], float (&v)[32], const float *s_bias, const GemmEpi &ep,
@@ -144,48 +236,6 @@ __device__ __forceinline__ void epilogue_drain(uint32_t t_addr, uint8_t *stg, co
     }
 }
 
-// + residual for one 32-column chunk: `rz` = the thread's 64 residual bf16 of these columns (4 x uint4 = 32 values), added in fp32;
-// RES == 2 recomputes LayerNorm(z_res) on the fly.  Then rounds to bf16, accumulates the row statistics of the ROUNDED values (what
-// the next GEMM will actually read) and leaves the packed pairs in pk[16].
-template <int RES>
-__device__ __forceinline__ void residual_pack(float (&v)[32], const uint4 (&rz)[4], const GemmEpi &ep, int col0_global, RowFold &rf,
-                                              uint32_t (&pk)[16])
-{
-    if constexpr (RES != 0) {
-        const uint32_t w[16] = {rz[0].x, rz[0].y, rz[0].z, rz[0].w, rz[1].x, rz[1].y, rz[1].z, rz[1].w,
-                                rz[2].x, rz[2].y, rz[2].z, rz[2].w, rz[3].x, rz[3].y, rz[3].z, rz[3].w};
-        if constexpr (RES == 2) {
-            const float4 *g4 = reinterpret_cast<const float4 *>(ep.res_gamma + col0_global);
-            const float4 *b4 = reinterpret_cast<const float4 *>(ep.res_beta + col0_global);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
-                const float z0 = __uint_as_float(w[2 * j] << 16), z1 = __uint_as_float(w[2 * j] & 0xffff0000u);
-                const float z2 = __uint_as_float(w[2 * j + 1] << 16), z3 = __uint_as_float(w[2 * j + 1] & 0xffff0000u);
-                v[4 * j + 0] += fmaf((z0 - rf.r_mu) * rf.r_rstd, g.x, b.x);
-                v[4 * j + 1] += fmaf((z1 - rf.r_mu) * rf.r_rstd, g.y, b.y);
-                v[4 * j + 2] += fmaf((z2 - rf.r_mu) * rf.r_rstd, g.z, b.z);
-                v[4 * j + 3] += fmaf((z3 - rf.r_mu) * rf.r_rstd, g.w, b.w);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                v[2 * j] += __uint_as_float(w[j] << 16);
-                v[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
-            }
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        pk[j] = tc::pack_bf16(v[2 * j], v[2 * j + 1]);
-        if constexpr (RES != 0) {
-            const float lo = __uint_as_float(pk[j] << 16), hi = __uint_as_float(pk[j] & 0xffff0000u);
-            rf.sum += lo + hi;
-            rf.sumsq = fmaf(lo, lo, fmaf(hi, hi, rf.sumsq));
-        }
-    }
-}
-
 // Drain of one warp's 32 rows x 128 columns (the pair kernel, BN = 256, bf16 output) with the LayerNorm fold: both 64-column chunks
 // unrolled so that the prefetched residual registers are indexed statically.
 template <int EPI, bool FOLD, int RES>
@@ -194,7 +244,7 @@ __device__ __forceinline__ void epilogue_drain_fold(uint32_t t_addr, uint8_t *st
                                                     RowFold &rf, const uint4 (&rz)[16])
 {
     uint32_t ra[32], rb[32], pk[16];
-    float v[32];
+    uint64_t v[16];
     tc::tmem_ld_32x32(t_addr + c_begin, ra);
 #pragma unroll
     for (int ci = 0; ci < 2; ++ci) {
@@ -214,19 +264,19 @@ __device__ __forceinline__ void epilogue_drain_fold(uint32_t t_addr, uint8_t *st
         }
         tc::tmem_ld_wait();
         tc::tmem_ld_32x32(t_addr + c + 32, rb);
-        epilogue_math<EPI, FOLD>(ra, v, s_bias + c, ep, n0 + c, ba, rf);
+        epilogue_math2<EPI, FOLD>(ra, v, s_bias + c, ep, n0 + c, ba, rf);
         {
             const uint4 r4[4] = {mine[0], mine[1], mine[2], mine[3]};
-            residual_pack<RES>(v, r4, ep, n0 + c, rf, pk);
+            residual_pack2<RES>(v, r4, ep, n0 + c, rf, pk);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) *staging_slot(stg, lane, j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         tc::tmem_ld_wait();
         if (ci == 0) tc::tmem_ld_32x32(t_addr + c + 64, ra);
-        epilogue_math<EPI, FOLD>(rb, v, s_bias + c + 32, ep, n0 + c + 32, ba, rf);
+        epilogue_math2<EPI, FOLD>(rb, v, s_bias + c + 32, ep, n0 + c + 32, ba, rf);
         {
             const uint4 r4[4] = {mine[4], mine[5], mine[6], mine[7]};
-            residual_pack<RES>(v, r4, ep, n0 + c + 32, rf, pk);
+            residual_pack2<RES>(v, r4, ep, n0 + c + 32, rf, pk);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) *staging_slot(stg, lane, 4 + j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
@@ -490,11 +540,16 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
             // this tile's bias slice -> smem (the previous tile's readers are past their last use: barrier below)
             tc::named_bar_sync(1, EPI_WARPS * 32);
-            for (int i = etid; i < BN; i += EPI_WARPS * 32) s_bias[i] = __ldg(ep.bias + n0 + i);
+            for (int i = etid; i < BN; i += EPI_WARPS * 32) {
+                float b = __ldg(ep.bias + n0 + i);
+                if constexpr (RES == 2) b += __ldg(ep.res_beta + n0 + i);      // beta of the recomputed LayerNorm residual rides with the bias
+                s_bias[i] = b;
+            }
             tc::named_bar_sync(1, EPI_WARPS * 32);
 
             // LayerNorm fold: this thread's row statistics and (RES) its 128-column residual slice, loaded before the accumulator wait
             RowFold rf = RowFold();
+            rf.sum2 = tc::f2_pack(0.0f, 0.0f); rf.sq2 = rf.sum2;
             uint4 rz[16];
             {
                 const int row = (row0 + lane < M) ? row0 + lane : M - 1;
@@ -541,7 +596,9 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 else tc::mbar_arrive_cluster(tc::mapa_u32(&tempty[acc], 0));
             }
             if constexpr (RES != 0) {
-                if (row0 + lane < M) ep.stats_out[(size_t)(row0 + lane) * 4 + (n0 / BN) * 2 + half] = make_float2(rf.sum, rf.sumsq);
+                float s_lo, s_hi, q_lo, q_hi;
+                tc::f2_unpack(rf.sum2, s_lo, s_hi); tc::f2_unpack(rf.sq2, q_lo, q_hi);
+                if (row0 + lane < M) ep.stats_out[(size_t)(row0 + lane) * 4 + (n0 / BN) * 2 + half] = make_float2(s_lo + s_hi, q_lo + q_hi);
             }
         }
         if (lane == 0) tc::tma_store_wait<0>();
