@@ -251,7 +251,7 @@ __device__ __forceinline__ void epilogue_drain_fold(uint32_t t_addr, uint8_t *st
         const int c = c_begin + ci * 64;
         // The residual chunk (32 rows x 128 B) was prefetched COALESCED (lane = 16-byte piece (lane & 7) of row 4 i + (lane >> 3)): it is
         // transposed to "thread = row" through this warp's staging tile, which the previous TMA store must have finished reading.
-        uint4 mine[8];
+        uint4 mine[8] = {};
         if (lane == 0) tc::tma_store_wait_read<0>();
         __syncwarp();
         if constexpr (RES != 0) {
@@ -413,17 +413,79 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // and writes each CTA's 128 accumulator rows into its own TMEM.  Per CTA and k-block this moves 32 KB instead of 48 KB
 // through L2 / the shared-memory ports for the same number of MACs, which is what lifts the 1-CTA kernel's ~66 % ceiling
 // (UMMA operand reads + TMA fills exceed 128 B/clk/SM there).
-template <int BN> struct Gemm2Cfg {
-    static constexpr int STAGES = 6;
+// RESID: the residual-adding kernels give two ring stages (64 KB) to a per-warp landing zone for the residual tile (cp.async)
+template <int BN, bool RESID = false> struct Gemm2Cfg {
+    static constexpr int STAGES = RESID ? 4 : 6;
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = (BN / 2) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
-    static constexpr int OFF_BIAS = OFF_STAGING + EPI_WARPS * STAGING_BYTES;
+    static constexpr int RESID_WARP_BYTES = 2 * STAGING_BYTES;                    // two 64-column chunks of 32 rows
+    static constexpr int OFF_RESID = OFF_STAGING + EPI_WARPS * STAGING_BYTES;
+    static constexpr int OFF_BIAS = OFF_RESID + (RESID ? EPI_WARPS * RESID_WARP_BYTES : 0);
     static constexpr int OFF_BARS = OFF_BIAS + BN * 4;
     static constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;
 };
+
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Drain of one warp's 32 rows x 128 columns for the residual-adding kernels.  The residual tile is NOT loaded by this function: it
+// arrives by cp.async in the warp's landing zone `rbuf` (same swizzled "row r, 16-byte piece c" layout as the staging tile, so that
+// "thread = row" reads are conflict free), one commit group per 64-column chunk, issued a whole chunk-drain ahead: as soon as chunk
+// ci of THIS tile has been read out, `next_chunk(ci)` issues chunk ci of the warp's NEXT tile into the same bytes.  The invariant
+// "exactly one younger group in flight" makes every wait a cp.async.wait_group 1.
+// Before: the 64 KB residual of a tile was fetched into registers at the top of the tile's epilogue and needed a few hundred clocks
+// later; with the accumulator already waiting (the RES kernels are not MMA bound) its whole DRAM latency sat on the epilogue's
+// critical path every tile -- ncu: DRAM 49 %, tensor pipe 34 %, neither bound.
+template <int EPI, bool FOLD, int RES, class NextChunk>
+__device__ __forceinline__ void epilogue_drain_res(uint32_t t_addr, uint8_t *stg, const uint8_t *rbuf, const float *s_bias, const GemmEpi &ep,
+                                                   const CUtensorMap *tmC, int n0, int row0, int ba, int c_begin, int lane, RowFold &rf,
+                                                   NextChunk &&next_chunk)
+{
+    uint32_t ra[32], rb[32], pk[16];
+    uint64_t v[16];
+    tc::tmem_ld_32x32(t_addr + c_begin, ra);
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci) {
+        const int c = c_begin + ci * 64;
+        uint4 mine[8];
+        cp_async_wait<1>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mine[j] = *staging_slot(const_cast<uint8_t *>(rbuf) + ci * STAGING_BYTES, lane, j);
+        __syncwarp();                                   // every lane has its row: the chunk's bytes may be refilled
+        next_chunk(ci);
+        tc::tmem_ld_wait();
+        tc::tmem_ld_32x32(t_addr + c + 32, rb);
+        epilogue_math2<EPI, FOLD>(ra, v, s_bias + c, ep, n0 + c, ba, rf);
+        {
+            const uint4 r4[4] = {mine[0], mine[1], mine[2], mine[3]};
+            residual_pack2<RES>(v, r4, ep, n0 + c, rf, pk);
+        }
+        if (lane == 0) tc::tma_store_wait_read<0>();    // the previous TMA store has read the output staging tile
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *staging_slot(stg, lane, j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        tc::tmem_ld_wait();
+        if (ci == 0) tc::tmem_ld_32x32(t_addr + c + 64, ra);
+        epilogue_math2<EPI, FOLD>(rb, v, s_bias + c + 32, ep, n0 + c + 32, ba, rf);
+        {
+            const uint4 r4[4] = {mine[4], mine[5], mine[6], mine[7]};
+            residual_pack2<RES>(v, r4, ep, n0 + c + 32, rf, pk);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *staging_slot(stg, lane, 4 + j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) { tc::tma_store_2d(tmC, stg, n0 + c, row0); tc::tma_store_commit(); }
+    }
+}
 
 //
 // LayerNorm fold (FOLD / RES template parameters; BN = 256 only).  The post-norm encoder layer is  y = LN1(h + attn(h)),
@@ -440,7 +502,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const GemmEpi ep, const int M, const int N, const int K)
 {
-    using Cfg = Gemm2Cfg<BN>;
+    using Cfg = Gemm2Cfg<BN, RES != 0>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::OFF_BARS);
@@ -524,7 +586,34 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int half = (warp - 2) >> 2;        // which half of the tile's BN columns this warp drains
         const int etid = (warp - 2) * 32 + lane;
         uint8_t *stg = smem + Cfg::OFF_STAGING + (warp - 2) * STAGING_BYTES;
-        int it = 0;
+        uint8_t *rbuf = smem + Cfg::OFF_RESID + (warp - 2) * Cfg::RESID_WARP_BYTES;      // RES != 0 only
+        // chunk (0 / 1 = the two 64-column halves of this warp's 128 columns) of the residual of tile t -> landing zone, coalesced:
+        // per instruction the warp copies 4 rows x 128 B (lane = 16-byte piece (lane & 7) of row 4 i + (lane >> 3))
+        auto issue_resid = [&](int t, int chunk) {
+            const int tm0 = (t / n_tiles) * (2 * BM) + (int)rank * BM + quarter * 32, tn0 = (t % n_tiles) * BN + half * (BN / 2) + chunk * 64;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int rr = tm0 + i * 4 + (lane >> 3);
+                if (rr >= M) rr = M - 1;
+                cp_async_16(staging_slot(rbuf + chunk * STAGING_BYTES, i * 4 + (lane >> 3), lane & 7),
+                            reinterpret_cast<const uint4 *>(ep.resid + (size_t)rr * N + tn0) + (lane & 7));
+            }
+            cp_async_commit();
+        };
+        auto load_res_stats = [&](int t, float4 &a, float4 &b) {
+            int row = (t / n_tiles) * (2 * BM) + (int)rank * BM + quarter * 32 + lane;
+            if (row >= M) row = M - 1;
+            const float4 *sp = reinterpret_cast<const float4 *>(ep.res_stats + (size_t)row * 4);
+            a = __ldg(sp); b = __ldg(sp + 1);
+        };
+        float4 nsa = make_float4(0.f, 0.f, 0.f, 0.f), nsb = nsa;          // RES == 2: row statistics of the residual, one tile ahead
+        if constexpr (RES != 0) {
+            if (pair < num_tiles) {
+                issue_resid(pair, 0); issue_resid(pair, 1);
+                if constexpr (RES == 2) load_res_stats(pair, nsa, nsb);
+            } else { cp_async_commit(); cp_async_commit(); }
+        }
+        int it = 0, bias_n0 = -1;
         for (int t = pair; t < num_tiles; t += n_pairs, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -538,19 +627,24 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const int r = (row - b * ep.tok_per_env) / ep.T;
                 ba = b * ep.A + (r % ep.A);
             }
-            // this tile's bias slice -> smem (the previous tile's readers are past their last use: barrier below)
-            tc::named_bar_sync(1, EPI_WARPS * 32);
-            for (int i = etid; i < BN; i += EPI_WARPS * 32) {
-                float b = __ldg(ep.bias + n0 + i);
-                if constexpr (RES == 2) b += __ldg(ep.res_beta + n0 + i);      // beta of the recomputed LayerNorm residual rides with the bias
-                s_bias[i] = b;
+            // this tile's bias slice -> smem, only when the column block changed (a pair of a 2-column-block GEMM keeps its block for
+            // the whole launch: n_pairs is even); the previous tile's readers are past their last use: barrier below
+            if (n0 != bias_n0) {
+                tc::named_bar_sync(1, EPI_WARPS * 32);
+                for (int i = etid; i < BN; i += EPI_WARPS * 32) {
+                    float b = __ldg(ep.bias + n0 + i);
+                    if constexpr (RES == 2) b += __ldg(ep.res_beta + n0 + i);      // beta of the recomputed LayerNorm residual rides with the bias
+                    s_bias[i] = b;
+                }
+                tc::named_bar_sync(1, EPI_WARPS * 32);
+                bias_n0 = n0;
             }
-            tc::named_bar_sync(1, EPI_WARPS * 32);
 
-            // LayerNorm fold: this thread's row statistics and (RES) its 128-column residual slice, loaded before the accumulator wait
+            // LayerNorm fold: this thread's row statistics, loaded before the accumulator wait
             RowFold rf = RowFold();
             rf.sum2 = tc::f2_pack(0.0f, 0.0f); rf.sq2 = rf.sum2;
-            uint4 rz[16];
+            const int t_next = t + n_pairs;
+            const bool has_next = t_next < num_tiles;
             {
                 const int row = (row0 + lane < M) ? row0 + lane : M - 1;
                 if constexpr (FOLD) {
@@ -561,30 +655,25 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     rf.rstd = rsqrtf(fmaxf(var, 0.0f) + 1e-5f);
                     rf.nmr = -rf.rstd * mu;
                 }
-                if constexpr (RES != 0) {
-                    // coalesced: per instruction the warp reads 4 rows x 128 B (four full lines) instead of 16 B from 32 different rows
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        int rr = row0 + (j & 7) * 4 + (lane >> 3);
-                        if (rr >= M) rr = M - 1;
-                        rz[j] = __ldg(reinterpret_cast<const uint4 *>(ep.resid + (size_t)rr * N + n0 + half * (BN / 2) + (j >> 3) * 64) + (lane & 7));
-                    }
-                    if constexpr (RES == 2) {
-                        const float4 *sp = reinterpret_cast<const float4 *>(ep.res_stats + (size_t)row * 4);
-                        const float4 a = __ldg(sp), b = __ldg(sp + 1);
-                        rf.r_mu = (a.x + a.z + b.x + b.z) * (1.0f / 512.0f);
-                        const float var = (a.y + a.w + b.y + b.w) * (1.0f / 512.0f) - rf.r_mu * rf.r_mu;
-                        rf.r_rstd = rsqrtf(fmaxf(var, 0.0f) + 1e-5f);
-                    }
+                if constexpr (RES == 2) {
+                    rf.r_mu = (nsa.x + nsa.z + nsb.x + nsb.z) * (1.0f / 512.0f);
+                    const float var = (nsa.y + nsa.w + nsb.y + nsb.w) * (1.0f / 512.0f) - rf.r_mu * rf.r_mu;
+                    rf.r_rstd = rsqrtf(fmaxf(var, 0.0f) + 1e-5f);
+                    if (has_next) load_res_stats(t_next, nsa, nsb);           // in flight during this tile's drain
                 }
             }
             tc::mbar_wait(&tfull[acc], acc_phase);
             __syncwarp();                 // reconverge before the .sync.aligned TMEM loads
             tc::tc_fence_after();
             const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
-            if constexpr (FOLD || RES != 0) {
+            if constexpr (RES != 0) {
                 static_assert(BN == 256, "the LayerNorm fold is written for 256-column tiles (two 64-column chunks per warp)");
-                epilogue_drain_fold<EPI, FOLD, RES>(t_addr, stg, s_bias, ep, &tmC, n0, row0, ba, half * (BN / 2), lane, rf, rz);
+                epilogue_drain_res<EPI, FOLD, RES>(t_addr, stg, rbuf, s_bias, ep, &tmC, n0, row0, ba, half * (BN / 2), lane, rf,
+                                                   [&](int chunk) { if (has_next) issue_resid(t_next, chunk); else cp_async_commit(); });
+            } else if constexpr (FOLD) {
+                static_assert(BN == 256, "the LayerNorm fold is written for 256-column tiles (two 64-column chunks per warp)");
+                const uint4 rz[16] = {};
+                epilogue_drain_fold<EPI, FOLD, 0>(t_addr, stg, s_bias, ep, &tmC, n0, row0, ba, half * (BN / 2), lane, rf, rz);
             } else {
                 epilogue_drain<EPI>(t_addr, stg, s_bias, ep, &tmC, n0, row0, ba, half * (BN / 2), (half + 1) * (BN / 2), lane);
             }
@@ -601,6 +690,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (row0 + lane < M) ep.stats_out[(size_t)(row0 + lane) * 4 + (n0 / BN) * 2 + half] = make_float2(s_lo + s_hi, q_lo + q_hi);
             }
         }
+        if constexpr (RES != 0) cp_async_wait<0>();
         if (lane == 0) tc::tma_store_wait<0>();
     }
     tc::tc_fence_before();
@@ -649,7 +739,7 @@ int launch_t(const GemmPlan *p, const GemmEpi *ep, int num_sms, cudaStream_t str
 template <int BN, int EPI, bool FOLD = false, int RES = 0>
 int launch2_t(const GemmPlan *p, const GemmEpi *ep, int num_sms, cudaStream_t stream)
 {
-    using Cfg = Gemm2Cfg<BN>;
+    using Cfg = Gemm2Cfg<BN, RES != 0>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
