@@ -51,15 +51,15 @@ struct RowFold {
 // the RES kernels (ncu: neither DRAM nor the tensor pipe above 55 %); packed it is about half of that.
 template <int EPI, bool FOLD>
 __device__ __forceinline__ void epilogue_math2(const uint32_t (&acc)[32], uint64_t (&v2)[16], const float *s_bias, const GemmEpi &ep,
-                                               int col0_global, int ba, const RowFold &rf)
+                                               int col0_global, int ba, const RowFold &rf, const float *s_colsum = nullptr)
 {
     const ulonglong2 *b2 = reinterpret_cast<const ulonglong2 *>(s_bias);
     if constexpr (FOLD) {
-        const ulonglong2 *c2 = reinterpret_cast<const ulonglong2 *>(ep.colsum + col0_global);
+        const ulonglong2 *c2 = reinterpret_cast<const ulonglong2 *>(s_colsum);   // shared memory (ncu: as eight LDG.128 per chunk it cost 6 % of the kernel)
         const uint64_t rstd2 = tc::f2_pack(rf.rstd, rf.rstd), nmr2 = tc::f2_pack(rf.nmr, rf.nmr);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const ulonglong2 b = b2[j], c = __ldg(c2 + j);
+            const ulonglong2 b = b2[j], c = c2[j];
             v2[2 * j] = tc::f2_fma(tc::f2_pack(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1])), rstd2, tc::f2_fma(nmr2, c.x, b.x));
             v2[2 * j + 1] = tc::f2_fma(tc::f2_pack(__uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3])), rstd2, tc::f2_fma(nmr2, c.y, b.y));
         }
@@ -236,48 +236,32 @@ __device__ __forceinline__ void epilogue_drain(uint32_t t_addr, uint8_t *stg, co
     }
 }
 
-// Drain of one warp's 32 rows x 128 columns (the pair kernel, BN = 256, bf16 output) with the LayerNorm fold: both 64-column chunks
-// unrolled so that the prefetched residual registers are indexed statically.
-template <int EPI, bool FOLD, int RES>
-__device__ __forceinline__ void epilogue_drain_fold(uint32_t t_addr, uint8_t *stg, const float *s_bias, const GemmEpi &ep,
-                                                    const CUtensorMap *tmC, int n0, int row0, int ba, int c_begin, int lane,
-                                                    RowFold &rf, const uint4 (&rz)[16])
+// Drain of one warp's 32 rows x 128 columns (the pair kernel, BN = 256, bf16 output) of a CONSUMING GEMM of the LayerNorm fold
+// (FOLD; the residual-adding kernels have their own drain below).  s_bias / s_colsum point into the kernel's shared-memory tables of
+// ALL N columns at this chunk's first column.
+template <int EPI, bool FOLD>
+__device__ __forceinline__ void epilogue_drain_fold(uint32_t t_addr, uint8_t *stg, const float *s_bias, const float *s_colsum, const GemmEpi &ep,
+                                                    const CUtensorMap *tmC, int n0, int row0, int ba, int c_begin, int lane, RowFold &rf)
 {
     uint32_t ra[32], rb[32], pk[16];
     uint64_t v[16];
+    const uint4 none[4] = {};
     tc::tmem_ld_32x32(t_addr + c_begin, ra);
 #pragma unroll
     for (int ci = 0; ci < 2; ++ci) {
         const int c = c_begin + ci * 64;
-        // The residual chunk (32 rows x 128 B) was prefetched COALESCED (lane = 16-byte piece (lane & 7) of row 4 i + (lane >> 3)): it is
-        // transposed to "thread = row" through this warp's staging tile, which the previous TMA store must have finished reading.
-        uint4 mine[8] = {};
-        if (lane == 0) tc::tma_store_wait_read<0>();
-        __syncwarp();
-        if constexpr (RES != 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) *staging_slot(stg, i * 4 + (lane >> 3), lane & 7) = rz[ci * 8 + i];
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) mine[j] = *staging_slot(stg, lane, j);
-            __syncwarp();
-        }
         tc::tmem_ld_wait();
         tc::tmem_ld_32x32(t_addr + c + 32, rb);
-        epilogue_math2<EPI, FOLD>(ra, v, s_bias + c, ep, n0 + c, ba, rf);
-        {
-            const uint4 r4[4] = {mine[0], mine[1], mine[2], mine[3]};
-            residual_pack2<RES>(v, r4, ep, n0 + c, rf, pk);
-        }
+        epilogue_math2<EPI, FOLD>(ra, v, s_bias + c, ep, n0 + c, ba, rf, s_colsum + c);
+        residual_pack2<0>(v, none, ep, n0 + c, rf, pk);
+        if (lane == 0) tc::tma_store_wait_read<0>();
+        __syncwarp();
 #pragma unroll
         for (int j = 0; j < 4; ++j) *staging_slot(stg, lane, j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         tc::tmem_ld_wait();
         if (ci == 0) tc::tmem_ld_32x32(t_addr + c + 64, ra);
-        epilogue_math2<EPI, FOLD>(rb, v, s_bias + c + 32, ep, n0 + c + 32, ba, rf);
-        {
-            const uint4 r4[4] = {mine[4], mine[5], mine[6], mine[7]};
-            residual_pack2<RES>(v, r4, ep, n0 + c + 32, rf, pk);
-        }
+        epilogue_math2<EPI, FOLD>(rb, v, s_bias + c + 32, ep, n0 + c + 32, ba, rf, s_colsum + c + 32);
+        residual_pack2<0>(v, none, ep, n0 + c + 32, rf, pk);
 #pragma unroll
         for (int j = 0; j < 4; ++j) *staging_slot(stg, lane, 4 + j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         tc::fence_proxy_async();
@@ -413,9 +397,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // and writes each CTA's 128 accumulator rows into its own TMEM.  Per CTA and k-block this moves 32 KB instead of 48 KB
 // through L2 / the shared-memory ports for the same number of MACs, which is what lifts the 1-CTA kernel's ~66 % ceiling
 // (UMMA operand reads + TMA fills exceed 128 B/clk/SM there).
-// RESID: the residual-adding kernels give two ring stages (64 KB) to a per-warp landing zone for the residual tile (cp.async)
-template <int BN, bool RESID = false> struct Gemm2Cfg {
-    static constexpr int STAGES = RESID ? 4 : 6;
+// MODE 0: plain epilogues, 6-stage operand ring.
+// MODE 1 (RES): the residual-adding kernels give two ring stages (64 KB) to a per-warp landing zone for the residual tile (cp.async).
+// MODE 2 (FOLD): the consuming kernels give one stage (32 KB) to bias / colsum tables of ALL N columns (no per-tile refill, no
+//         barrier per tile, no global loads in the drain) and to a per-warp landing zone for the row statistics of the next tile.
+constexpr int FOLD_MAX_N = 1536;
+template <int BN, int MODE = 0> struct Gemm2Cfg {
+    static constexpr int STAGES = MODE == 1 ? 4 : (MODE == 2 ? 5 : 6);
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = (BN / 2) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -423,10 +411,14 @@ template <int BN, bool RESID = false> struct Gemm2Cfg {
     static constexpr int OFF_STAGING = STAGES * STAGE_BYTES;
     static constexpr int RESID_WARP_BYTES = 2 * STAGING_BYTES;                    // two 64-column chunks of 32 rows
     static constexpr int OFF_RESID = OFF_STAGING + EPI_WARPS * STAGING_BYTES;
-    static constexpr int OFF_BIAS = OFF_RESID + (RESID ? EPI_WARPS * RESID_WARP_BYTES : 0);
+    static constexpr int OFF_COLT = OFF_RESID + (MODE == 1 ? EPI_WARPS * RESID_WARP_BYTES : 0);     // MODE 2: bias[FOLD_MAX_N], colsum[FOLD_MAX_N]
+    static constexpr int STATS_WARP_BYTES = 2 * 32 * 32;                          // two tiles x 32 rows x (4 x float2)
+    static constexpr int OFF_STATS = OFF_COLT + (MODE == 2 ? 2 * FOLD_MAX_N * 4 : 0);
+    static constexpr int OFF_BIAS = OFF_STATS + (MODE == 2 ? EPI_WARPS * STATS_WARP_BYTES : 0);
     static constexpr int OFF_BARS = OFF_BIAS + BN * 4;
     static constexpr int SMEM_BYTES = OFF_BARS + 256 + 1024;
 };
+static_assert(Gemm2Cfg<256, 2>::SMEM_BYTES <= 227 * 1024 && Gemm2Cfg<256, 1>::SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src)
 {
@@ -502,7 +494,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const GemmEpi ep, const int M, const int N, const int K)
 {
-    using Cfg = Gemm2Cfg<BN, RES != 0>;
+    using Cfg = Gemm2Cfg<BN, RES != 0 ? 1 : (FOLD ? 2 : 0)>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::OFF_BARS);
@@ -606,6 +598,23 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const float4 *sp = reinterpret_cast<const float4 *>(ep.res_stats + (size_t)row * 4);
             a = __ldg(sp); b = __ldg(sp + 1);
         };
+        // FOLD: bias / colsum of all N columns -> shared memory once; row statistics of the NEXT tile by cp.async (32 bytes per row, each
+        // thread lands and later reads its own row: no warp synchronisation needed, one commit group per tile, wait_group 1)
+        float *s_ball = reinterpret_cast<float *>(smem + Cfg::OFF_COLT), *s_call = s_ball + FOLD_MAX_N;
+        uint8_t *sbuf = smem + Cfg::OFF_STATS + (warp - 2) * Cfg::STATS_WARP_BYTES;
+        auto issue_stats = [&](int t, int buf) {
+            int row = (t / n_tiles) * (2 * BM) + (int)rank * BM + quarter * 32 + lane;
+            if (row >= M) row = M - 1;
+            const float4 *sp = reinterpret_cast<const float4 *>(ep.stats_in + (size_t)row * 4);
+            cp_async_16(sbuf + buf * 1024 + lane * 32, sp);
+            cp_async_16(sbuf + buf * 1024 + lane * 32 + 16, sp + 1);
+            cp_async_commit();
+        };
+        if constexpr (FOLD) {
+            for (int i = etid; i < N; i += EPI_WARPS * 32) { s_ball[i] = __ldg(ep.bias + i); s_call[i] = __ldg(ep.colsum + i); }
+            tc::named_bar_sync(1, EPI_WARPS * 32);
+            if (pair < num_tiles) issue_stats(pair, 0); else cp_async_commit();
+        }
         float4 nsa = make_float4(0.f, 0.f, 0.f, 0.f), nsb = nsa;          // RES == 2: row statistics of the residual, one tile ahead
         if constexpr (RES != 0) {
             if (pair < num_tiles) {
@@ -629,7 +638,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
             // this tile's bias slice -> smem, only when the column block changed (a pair of a 2-column-block GEMM keeps its block for
             // the whole launch: n_pairs is even); the previous tile's readers are past their last use: barrier below
-            if (n0 != bias_n0) {
+            if (!FOLD && n0 != bias_n0) {
                 tc::named_bar_sync(1, EPI_WARPS * 32);
                 for (int i = etid; i < BN; i += EPI_WARPS * 32) {
                     float b = __ldg(ep.bias + n0 + i);
@@ -646,10 +655,11 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const int t_next = t + n_pairs;
             const bool has_next = t_next < num_tiles;
             {
-                const int row = (row0 + lane < M) ? row0 + lane : M - 1;
                 if constexpr (FOLD) {
-                    const float4 *sp = reinterpret_cast<const float4 *>(ep.stats_in + (size_t)row * 4);
-                    const float4 a = __ldg(sp), b = __ldg(sp + 1);
+                    if (has_next) issue_stats(t_next, (it + 1) & 1); else cp_async_commit();
+                    cp_async_wait<1>();                                       // this tile's statistics (requested a tile ago) have landed
+                    const float4 a = *reinterpret_cast<const float4 *>(sbuf + (it & 1) * 1024 + lane * 32);
+                    const float4 b = *reinterpret_cast<const float4 *>(sbuf + (it & 1) * 1024 + lane * 32 + 16);
                     const float mu = (a.x + a.z + b.x + b.z) * (1.0f / 512.0f);
                     const float var = (a.y + a.w + b.y + b.w) * (1.0f / 512.0f) - mu * mu;
                     rf.rstd = rsqrtf(fmaxf(var, 0.0f) + 1e-5f);
@@ -672,8 +682,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                                    [&](int chunk) { if (has_next) issue_resid(t_next, chunk); else cp_async_commit(); });
             } else if constexpr (FOLD) {
                 static_assert(BN == 256, "the LayerNorm fold is written for 256-column tiles (two 64-column chunks per warp)");
-                const uint4 rz[16] = {};
-                epilogue_drain_fold<EPI, FOLD, 0>(t_addr, stg, s_bias, ep, &tmC, n0, row0, ba, half * (BN / 2), lane, rf, rz);
+                epilogue_drain_fold<EPI, FOLD>(t_addr, stg, s_ball + n0, s_call + n0, ep, &tmC, n0, row0, ba, half * (BN / 2), lane, rf);
             } else {
                 epilogue_drain<EPI>(t_addr, stg, s_bias, ep, &tmC, n0, row0, ba, half * (BN / 2), (half + 1) * (BN / 2), lane);
             }
@@ -690,7 +699,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 if (row0 + lane < M) ep.stats_out[(size_t)(row0 + lane) * 4 + (n0 / BN) * 2 + half] = make_float2(s_lo + s_hi, q_lo + q_hi);
             }
         }
-        if constexpr (RES != 0) cp_async_wait<0>();
+        if constexpr (RES != 0 || FOLD) cp_async_wait<0>();
         if (lane == 0) tc::tma_store_wait<0>();
     }
     tc::tc_fence_before();
@@ -739,7 +748,7 @@ int launch_t(const GemmPlan *p, const GemmEpi *ep, int num_sms, cudaStream_t str
 template <int BN, int EPI, bool FOLD = false, int RES = 0>
 int launch2_t(const GemmPlan *p, const GemmEpi *ep, int num_sms, cudaStream_t stream)
 {
-    using Cfg = Gemm2Cfg<BN, RES != 0>;
+    using Cfg = Gemm2Cfg<BN, RES != 0 ? 1 : (FOLD ? 2 : 0)>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
@@ -748,7 +757,7 @@ int launch2_t(const GemmPlan *p, const GemmEpi *ep, int num_sms, cudaStream_t st
     SNB_CUDA_TRY(attr_err);
     const int tiles = ((p->M + 2 * BM - 1) / (2 * BM)) * (p->N / BN);
     const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
-    if (FOLD) SNB_REQUIRE(ep->colsum && ep->stats_in && p->K == 512, SNB_EINVAL, "gemm: LayerNorm fold needs colsum / stats_in and K = 512");
+    if (FOLD) SNB_REQUIRE(ep->colsum && ep->stats_in && p->K == 512 && p->N <= FOLD_MAX_N, SNB_EINVAL, "gemm: LayerNorm fold needs colsum / stats_in, K = 512 and N <= 1536");
     if (RES) SNB_REQUIRE(ep->resid && ep->stats_out && p->N == 512 && (RES == 1 || (ep->res_stats && ep->res_gamma && ep->res_beta)), SNB_EINVAL,
                          "gemm: residual epilogue needs resid / stats_out (N = 512) and, for a normalised residual, its stats / gamma / beta");
     gemm2_bf16_tn_kernel<BN, EPI, FOLD, RES><<<2 * pairs, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(p->tmA, p->tmB2, p->tmC, *ep, p->M, p->N, p->K);
