@@ -403,7 +403,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 //         barrier per tile, no global loads in the drain) and to a per-warp landing zone for the row statistics of the next tile.
 constexpr int FOLD_MAX_N = 1536;
 template <int BN, int MODE = 0> struct Gemm2Cfg {
-    static constexpr int STAGES = MODE == 1 ? 4 : (MODE == 2 ? 5 : 6);
+#ifndef SNB_RES_STAGES
+#define SNB_RES_STAGES 4
+#endif
+    static constexpr int STAGES = MODE == 1 ? SNB_RES_STAGES : (MODE == 2 ? 5 : 6);
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = (BN / 2) * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
