@@ -373,6 +373,13 @@ int snb_pred_mpc_pack(const double *robot_dev, const double *humans_dev, const d
  *       (humans + robot, BEFORE the step) into slot `slot` of log_dev [B, L, H+1, 2] (entry H = robot);
  *   snb_pred_bootstrap_history: fills the predictor's rings from the L-deep log whose newest slot is `newest`. */
 int snb_env_log_push(const SnbCrowdState *state, double *log_dev, int32_t L, int32_t slot, void *stream);
+/* snb_env_step with the log push folded into the same launch: ring slot `slot` of log_dev [B, L, H + 1, 2] receives the positions
+ * BEFORE the step (what `self.states.append` holds for this step, crowd_sim_plus.py:1175-1181), of every environment, frozen or not. */
+int snb_env_step_logged(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const SnbRewardCfg *reward_cfg,
+                        const SnbCrowdState *state, const SnbObstacles *obs, const double *robot_action_dev,
+                        const uint8_t *active_dev, double *reward_dev, double *dmin_dev, int32_t *flags_dev,
+                        int32_t *nbr_dev, int32_t *nbr_cnt_dev, int32_t *status_dev, double *log_dev, int32_t L, int32_t slot,
+                        void *stream);
 int snb_pred_bootstrap_history(SnbPredictor *p, const double *log_dev, int32_t L, int32_t newest, int32_t B, void *stream);
 
 #ifdef __cplusplus

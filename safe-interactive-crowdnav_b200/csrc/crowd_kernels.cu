@@ -202,6 +202,8 @@ struct CrowdParams {
     int thread_mode;    // phase 1: 0 = one warp per human (small launches), 1 = one thread per human (large batches)
     int fast_lines;     // thread mode, plain ORCA: half-planes of every thread in shared memory (this many per thread), no local memory
     int lp3_mode;       // warp-owns-environments kernel: 0 = lp3_warp (loop per half-plane), 1 = lp3_warp_skip (ballot scans)
+    double *log;        // optional state log [B, log_L, H + 1, 2]: slot log_slot <- positions before the step (humans, then the robot)
+    int log_L, log_slot;
 };
 
 struct Line { float px, py, dx, dy; };
@@ -1646,6 +1648,18 @@ __global__ void __launch_bounds__(CROWD_THREADS, 3) crowd_step_kernel(const Crow
     if (aligned) mbar_wait(bar, 0);
     __syncthreads();
 
+    if (P.log) {                               // CrowdSimPlus.step's states.append: the positions this step starts from
+        for (int k = tid; k < nA; k += blockDim.x) {
+            const int e = k / H, h = k - e * H;
+            double *o = P.log + (((size_t)(env0 + e) * P.log_L + P.log_slot) * (H + 1) + h) * 2;
+            o[0] = T.px[k]; o[1] = T.py[k];
+        }
+        for (int k = tid; k < nenv; k += blockDim.x) {
+            double *o = P.log + (((size_t)(env0 + k) * P.log_L + P.log_slot) * (H + 1) + H) * 2;
+            o[0] = T.ex_px[k * E]; o[1] = T.ex_py[k * E];
+        }
+    }
+
     // ---- phase 1 (large batches): one thread per human ----
     if (P.thread_mode) {
         for (int task = tid; task < nA; task += blockDim.x) {
@@ -1890,6 +1904,10 @@ __global__ void __launch_bounds__(32 * FW_WARPS) crowd_orca_warp_kernel(const Cr
         T.px[lane] = my_px; T.py[lane] = my_py; T.vx[lane] = vx; T.vy[lane] = vy; T.rad[lane] = my_rad;
         fs[lane] = make_float4((float)my_px, (float)my_py, (float)vx, (float)vy);
         fr[lane] = (float)(my_rad + rad_pad);
+        if (P.log) {
+            double *o = P.log + (((size_t)genv * P.log_L + P.log_slot) * (H + 1) + i) * 2;
+            o[0] = my_px; o[1] = my_py;
+        }
     }
     if (lane < nenv * E) {
         const size_t x = (size_t)env0 * E + lane;
@@ -1897,6 +1915,10 @@ __global__ void __launch_bounds__(32 * FW_WARPS) crowd_orca_warp_kernel(const Cr
         T.ex_px[lane] = a; T.ex_py[lane] = b; T.ex_vx[lane] = c; T.ex_vy[lane] = d; T.ex_rad[lane] = r;
         fs[32 + lane] = make_float4((float)a, (float)b, (float)c, (float)d);
         fr[32 + lane] = (float)(r + rad_pad);
+        if (P.log) {                                        // E == 1 in this kernel: lane = environment, the extra is the robot
+            double *o = P.log + (((size_t)(env0 + lane) * P.log_L + P.log_slot) * (H + 1) + H) * 2;
+            o[0] = a; o[1] = b;
+        }
     }
     __syncwarp();
 
@@ -2043,7 +2065,8 @@ static size_t crowd_smem_bytes(int epc, int H, int E, int n_seg, int fast_lines 
 static int launch_crowd(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const SnbRewardCfg *rcfg, const SnbCrowdState *st,
                         const SnbObstacles *obs, const double *robot_action, const uint8_t *active, double *reward,
                         double *dmin, int *flags, double *out_v, int *nbr, int *nbr_cnt, int *status, int full_step, void *stream,
-                        int n_actions = 1, double *next_h = nullptr, double *next_robot = nullptr)
+                        int n_actions = 1, double *next_h = nullptr, double *next_robot = nullptr, double *log = nullptr, int log_L = 0,
+                        int log_slot = 0)
 {
     SNB_REQUIRE(cfg && st, SNB_EINVAL, "crowd step: cfg/state is NULL");
     SNB_REQUIRE(st->B >= 0 && st->H >= 1 && st->E >= 0, SNB_EINVAL, "crowd step: bad sizes B=%d H=%d E=%d", st->B, st->H, st->E);
@@ -2094,6 +2117,7 @@ static int launch_crowd(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const S
     }
     P.full_step = full_step;
     P.n_actions = n_actions; P.next_h = next_h; P.next_robot = next_robot;
+    P.log = log; P.log_L = log_L; P.log_slot = log_slot;
     if (P.thread_mode && P.n_vert == 0 && cfg->policy != SNB_POLICY_SFM && st->H - 1 + st->n_obs_extras <= FAST_MAXO &&
         cfg->max_neighbors >= 1 && cfg->max_neighbors <= FAST_LCAP && !getenv("SNB_CROWD_NO_FAST") &&
         crowd_smem_bytes(P.epc, st->H, st->E, P.n_seg, cfg->max_neighbors) <= 96 * 1024)
@@ -2136,6 +2160,18 @@ extern "C" int snb_policy_step(const SnbPolicyCfg *cfg, const SnbCrowdState *sta
 {
     return launch_crowd(cfg, nullptr, nullptr, state, obs, nullptr, nullptr, nullptr, nullptr, nullptr, out_v_dev, nbr_dev,
                         nbr_cnt_dev, status_dev, 0, stream);
+}
+
+extern "C" int snb_env_step_logged(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const SnbRewardCfg *reward_cfg,
+                                   const SnbCrowdState *state, const SnbObstacles *obs, const double *robot_action_dev,
+                                   const uint8_t *active_dev, double *reward_dev, double *dmin_dev, int32_t *flags_dev,
+                                   int32_t *nbr_dev, int32_t *nbr_cnt_dev, int32_t *status_dev, double *log_dev, int32_t L, int32_t slot,
+                                   void *stream)
+{
+    SNB_REQUIRE(log_dev && L >= 1 && slot >= 0 && slot < L, SNB_EINVAL, "snb_env_step_logged: bad log / ring slot");
+    SNB_REQUIRE(state && state->E == 1, SNB_EINVAL, "snb_env_step_logged: the simulator state has exactly one extra (the robot)");
+    return launch_crowd(cfg, door, reward_cfg, state, obs, robot_action_dev, active_dev, reward_dev, dmin_dev, flags_dev,
+                        nullptr, nbr_dev, nbr_cnt_dev, status_dev, 1, stream, 1, nullptr, nullptr, log_dev, L, slot);
 }
 
 extern "C" int snb_env_step(const SnbPolicyCfg *cfg, const SnbDoorCfg *door, const SnbRewardCfg *reward_cfg,

@@ -143,6 +143,8 @@ _proto("snb_pred_ingest", C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _d, 
 _proto("snb_pred_set_position_std", C.c_int, [_vp, _d], required=False)
 _proto("snb_pred_mpc_pack", C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
        required=False)
+_proto("snb_env_step_logged", C.c_int, [C.POINTER(PolicyCfg), C.POINTER(DoorCfg), C.POINTER(RewardCfg), C.POINTER(CrowdState),
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp])
 _proto("snb_env_log_push", C.c_int, [C.POINTER(CrowdState), _vp, _i32, _i32, _vp], required=False)
 _proto("snb_pred_bootstrap_history", C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp], required=False)
 

@@ -198,10 +198,16 @@ class CrowdSimPlusBatch:
             self._argc_tail = (_capi.ptr(self.reward), _capi.ptr(self.dmin), _capi.ptr(self.flags))
             self._argc_status = _capi.ptr(self.status)
         pc, dc, rc, st = self._argc
-        if self.state_log is not None:
-            _capi.check(_capi.lib.snb_env_log_push(C.byref(st), _capi.ptr(self.state_log), self.LOG_DEPTH, self.n_logged % self.LOG_DEPTH,
-                                                   _capi.stream_ptr(stream)), "snb_env_log_push")
+        if self.state_log is not None:        # states.append of this step rides in the same launch
+            slot = self.n_logged % self.LOG_DEPTH
             self.n_logged += 1
+            _capi.check(_capi.lib.snb_env_step_logged(pc, dc, rc, C.byref(st),
+                                                      self.obstacles.handle if self.obstacles is not None else None,
+                                                      _capi.ptr(action), _capi.ptr(active), *self._argc_tail,
+                                                      _capi.ptr(nbr), _capi.ptr(nbr_cnt), self._argc_status,
+                                                      _capi.ptr(self.state_log), self.LOG_DEPTH, slot,
+                                                      _capi.stream_ptr(stream)), "snb_env_step_logged")
+            return
         _capi.check(_capi.lib.snb_env_step(pc, dc, rc, C.byref(st),
                                            self.obstacles.handle if self.obstacles is not None else None,
                                            _capi.ptr(action), _capi.ptr(active), *self._argc_tail,

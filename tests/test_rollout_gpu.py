@@ -207,3 +207,23 @@ def test_orca_hbm_sized_batch_replicas_stay_bit_identical_and_match_the_oracle()
     for n in ("px", "py", "vx", "vy"):
         got = getattr(st, n)[:R].cpu().numpy().ravel()
         assert np.array_equal(got, getattr(oenv, n)), (n, np.max(np.abs(got - getattr(oenv, n))))
+
+
+@pytest.mark.parametrize("B", [64, 4096])
+def test_state_log_written_by_the_step_launch(B):
+    """CrowdSimPlus.step appends the state it starts from to self.states (crowd_sim_plus.py:1175-1181); here the ring slot is written by
+    the step's own launch (snb_env_step_logged) -- by crowd_step_kernel for 64 environments, by crowd_orca_warp_kernel for 4096."""
+    H = 10
+    env = _env(B, H, 30)
+    env.freeze_done = True                      # frozen environments are logged too
+    env.reset('test', test_cases=np.arange(B) % 500)
+    assert env.n_logged == 10                   # the starts_moving warm-up steps
+    st = env.state
+    act = torch.zeros(B, 2, dtype=torch.float64, device="cuda"); act[:, 1] = 1.0
+    env.active[::3] = 0
+    for k in range(9):                          # wraps the 7-slot ring
+        before = torch.cat([torch.stack([st.px, st.py], -1), torch.stack([st.ex_px, st.ex_py], -1)], 1).clone()   # [B, H + 1, 2]
+        slot = env.n_logged % env.LOG_DEPTH
+        env.step(act)
+        assert torch.equal(env.state_log[:, slot], before), k
+    env.check_status()
