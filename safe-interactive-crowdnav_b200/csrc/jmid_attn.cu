@@ -66,6 +66,9 @@ template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile
 #ifndef SNB_ATTN_POLY_EVERY
 #define SNB_ATTN_POLY_EVERY 4
 #endif
+#ifndef SNB_ATTN_PV_WAIT_AFTER
+#define SNB_ATTN_PV_WAIT_AFTER 1
+#endif
 #ifndef SNB_ATTN_LAG_AT
 #define SNB_ATTN_LAG_AT 1      // tile B starts when tile A has finished this many quarters (+1) of its first block's exponentials
 #endif
@@ -116,7 +119,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             tc::mbar_init(&s_full[s], 1); tc::mbar_init(&s_free[s], 128); tc::mbar_init(&p_ready[s], 128); tc::mbar_init(&pv_done[s], 1);
         }
         tc::mbar_init(lag, 128);
-        for (int s = 0; s < ATTN_RING; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1); }
+        for (int s = 0; s < ATTN_RING; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 2); }   // kv_empty: both issuers
         tc::fence_barrier_init();
     }
     if (warp == 2) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -159,8 +162,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                     load(cv, j);
                 }
             }
-        } else if (warp == 1) {
-          // ===================== MMA issuer =====================
+        } else if (warp == 1 || warp == 3) {
+          // ===================== MMA issuers: warp 1 issues tile A's MMAs, warp 3 tile B's =====================
+          // One issuer per tile: with a single in-order issuer S_A(j+1) queued behind the wait for P_B(j-1) and PV_A(j) behind the
+          // wait for S_B(j)'s consumer, which tied the two tiles together and pulled the half-block offset set up by `lag` back to
+          // ~500 clk within three blocks (trace of the de-phased kernel) -- the softmaxes then ran in phase again and shared the MUFU
+          // pipe.  Independent issuers only meet in the K/V ring: a slot is released when BOTH have committed their MMAs on it.
+          const int t = warp == 1 ? 0 : 1;
           // tmem_base comes out of shared memory; the broadcast makes it (and every address derived from it) provably
           // warp-uniform, so the tcgen05.mma operands live in uniform registers instead of being converted per instruction
           const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
@@ -214,45 +222,44 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 ++c;
                 tc::mbar_wait(&kv_full[slot], ph);
             };
-            int g[2] = {0, 0}, it[2] = {0, 0};           // per tile: iterations / items done so far (barrier phases)
+            int g = 0, it = 0;                           // iterations / items of MY tile so far (barrier phases)
             for (int w = blockIdx.x; w < args.n_items; w += gridDim.x) {
                 int q0, head, env; bool has_b;
                 decode(w, q0, head, env, has_b);
-                const int nt = has_b ? 2 : 1;
+                const bool mine = t == 0 || has_b;       // an item without a second tile: tile B's issuer only releases the ring slots
                 next_tile();                             // K0
-                for (int t = 0; t < nt; ++t) {
-                    tc::mbar_wait(&q_full[t], it[t] & 1);
-                    if (g[t] > 0) tc::mbar_wait(&s_free[t], (g[t] - 1) & 1);   // the previous item's last S_t is in registers
+                if (mine) {
+                    tc::mbar_wait(&q_full[t], it & 1);
+                    if (g > 0) tc::mbar_wait(&s_free[t], (g - 1) & 1);   // the previous item's last S_t is in registers
                     tc::tc_fence_after();
                     issue_S(t, slot, 0);
                     if (n_kv == 1) tc::umma_commit(&q_empty[t]);
-                }
-                tc::umma_commit(&kv_empty[slot]);
+                    tc::umma_commit(&kv_empty[slot]);
+                } else tc::mbar_arrive(&kv_empty[slot]);
                 for (int j = 0; j < n_kv; ++j) {
-                    if (j + 1 < n_kv) {                      // S(j+1) of both tiles as soon as the softmax warps hold S(j) in registers
+                    if (j + 1 < n_kv) {                      // S(j+1) as soon as the softmax warps hold S(j) in registers
                         next_tile();                         // K(j+1)
-                        for (int t = 0; t < nt; ++t) {
-                            tc::mbar_wait(&s_free[t], (g[t] + j) & 1);
+                        if (mine) {
+                            tc::mbar_wait(&s_free[t], (g + j) & 1);
                             tc::tc_fence_after();
-                            if (t == 0) ATTN_TRACE(4, j, 0);
+                            ATTN_TRACE(4, j, t == 0 ? 0 : 2);
                             issue_S(t, slot, j + 1);
                             if (j + 2 == n_kv) tc::umma_commit(&q_empty[t]);   // that was the item's last use of Q_t
-                        }
-                        tc::umma_commit(&kv_empty[slot]);
-                        ATTN_TRACE(4, j, 2);
+                            tc::umma_commit(&kv_empty[slot]);
+                        } else tc::mbar_arrive(&kv_empty[slot]);
                     }
                     next_tile();                             // V(j)
-                    for (int t = 0; t < nt; ++t) {
-                        if (j == 0) tc::mbar_wait(&o_free[t], (it[t] & 1) ^ 1);   // the previous item's O_t has been written out
-                        tc::mbar_wait(&p_ready[t], (g[t] + j) & 1);
+                    if (mine) {
+                        if (j == 0) tc::mbar_wait(&o_free[t], (it & 1) ^ 1);   // the previous item's O_t has been written out
+                        tc::mbar_wait(&p_ready[t], (g + j) & 1);
                         tc::tc_fence_after();
                         ATTN_TRACE(4, j, 3 + 2 * t);
                         issue_PV(t, slot, j);
                         ATTN_TRACE(4, j, 4 + 2 * t);
-                    }
-                    tc::umma_commit(&kv_empty[slot]);
+                        tc::umma_commit(&kv_empty[slot]);
+                    } else tc::mbar_arrive(&kv_empty[slot]);
                 }
-                for (int t = 0; t < nt; ++t) { g[t] += n_kv; ++it[t]; }
+                if (mine) { g += n_kv; ++it; }
             }
           }
         }
@@ -380,22 +387,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 // 32 KB tile (>= 256 clk of store bandwidth per tile) underneath the MUFU / FMA work of the next quarter instead of
                 // after all of it (the trace of the exps-then-stores order: 471 clk of the block's 2930 on the stores alone).
                 // PV_t(j-1) must have consumed the previous P first -- it was issued a whole softmax ago.
+                // P(j) may only be stored once PV_t(j-1) has consumed P(j-1).  That MMA was issued a whole softmax ago but queues behind the
+                // other tile's MMAs, and ncu's source view charged 8 % of all stall samples to this wait when it sat after the first
+                // quarter; the packed exponentials stay in the registers of the scores they replace, so the wait (and the stores of the
+                // quarters computed so far) can sit later at no register cost: SNB_ATTN_PV_WAIT_AFTER quarters of exponentials first.
+                auto wait_p_free = [&]() {
+                    if (g + j > 0) tc::mbar_wait(&pv_done[t], ph ^ 1);   // (for j == 0: the previous item's last PV, already awaited by its epilogue)
+                    if (j == 0 && g > 0) {
+                        // the previous item's O tile was staged in this P tile: its TMA store must have finished READING it
+                        if (row_in_tile == 0) tc::tma_store_wait_read<0>();
+                        tc::named_bar_sync(1 + t, 128);
+                    }
+                };
                 exp_pack(s0);
-                if (g + j > 0) tc::mbar_wait(&pv_done[t], ph ^ 1);   // (for j == 0: the previous item's last PV, already awaited by its epilogue)
-                if (j == 0 && g > 0) {
-                    // the previous item's O tile was staged in this P tile: its TMA store must have finished READING it
-                    if (row_in_tile == 0) tc::tma_store_wait_read<0>();
-                    tc::named_bar_sync(1 + t, 128);
-                }
-                store(s0, 0, 0);
+                if (SNB_ATTN_PV_WAIT_AFTER == 1) { wait_p_free(); store(s0, 0, 0); }
 #if !defined(SNB_ATTN_NO_LAG) && SNB_ATTN_LAG_AT == 0
                 if (t == 0 && j == 0 && has_b) tc::mbar_arrive(lag);
 #endif
-                exp_pack(s1); store(s1, 0, 4);
+                exp_pack(s1);
+                if (SNB_ATTN_PV_WAIT_AFTER == 2) { wait_p_free(); store(s0, 0, 0); }
+                if (SNB_ATTN_PV_WAIT_AFTER <= 2) store(s1, 0, 4);
 #if !defined(SNB_ATTN_NO_LAG) && SNB_ATTN_LAG_AT == 1
                 if (t == 0 && j == 0 && has_b) tc::mbar_arrive(lag);
 #endif
-                exp_pack(s2); store(s2, 1, 0);
+                exp_pack(s2);
+                if (SNB_ATTN_PV_WAIT_AFTER == 3) { wait_p_free(); store(s0, 0, 0); store(s1, 0, 4); }
+                store(s2, 1, 0);
 #if !defined(SNB_ATTN_NO_LAG) && SNB_ATTN_LAG_AT == 2
                 if (t == 0 && j == 0 && has_b) tc::mbar_arrive(lag);
 #endif
