@@ -8,6 +8,7 @@ Two faces over the same C ABI:
 torch tensors only hold weights and I/O buffers; every computation is in libsnb.so (no CPU path).
 """
 import ctypes as C
+import threading
 
 import numpy as np
 import torch
@@ -330,20 +331,25 @@ class HumanTrajectoryForecasterSim:
         self.mid_env = None          # the Trajectron Environment object has no counterpart: scenes are built on the device
         self.prev_states = [[] for _ in range(self.num_hums)]
         self.prev_robot_states = []
+        self.prev_states_lock = threading.Lock()      # mid_sim_wrapper.py:174: the histories may be appended from another thread (ROS callback)
 
     def update_state_hists(self, robot_state, human_states, time_stamp):
-        for i in range(self.num_hums):
-            self.prev_states[i].append([*human_states[i].position, time_stamp])
-            if len(self.prev_states[i]) > self.num_hist_frames:
-                self.prev_states[i].pop(0)
-        self.prev_robot_states.append([*robot_state.position, time_stamp])
-        if len(self.prev_robot_states) > self.num_hist_frames:   # the reference keeps it unbounded but only uses the joined tail
-            self.prev_robot_states.pop(0)
+        with self.prev_states_lock:
+            for i in range(self.num_hums):
+                self.prev_states[i].append([*human_states[i].position, time_stamp])
+                if len(self.prev_states[i]) > self.num_hist_frames:
+                    self.prev_states[i].pop(0)
+            self.prev_robot_states.append([*robot_state.position, time_stamp])
+            if len(self.prev_robot_states) > self.num_hist_frames:   # the reference keeps it unbounded but only uses the joined tail
+                self.prev_robot_states.pop(0)
 
     def _histories(self):
         """The joined, resampled frame table of mid_sim_wrapper.py:244-298 (identity when the frames are time_step apart)."""
         from .history import resample_histories
-        hum, rob = resample_histories(self.prev_states, self.prev_robot_states, self.time_step, self.num_hist_frames)
+        with self.prev_states_lock:                  # snapshot under the lock, like _gen_agent_df (mid_sim_wrapper.py:251-258)
+            prev = [list(p) for p in self.prev_states]
+            prev_robot = list(self.prev_robot_states)
+        hum, rob = resample_histories(prev, prev_robot, self.time_step, self.num_hist_frames)
         if hum.shape[1] < self.num_hist_frames:
             raise _capi.SnbError(f"snb predictor: {hum.shape[1]} frames are left after resampling the histories to time_step "
                                  f"(poses recorded faster than time_step, or stamps missing from an agent); the device pipeline "
