@@ -84,3 +84,29 @@ def test_scenario_generator_reproduces_reference_scenes():
             assert np.array_equal(sc["segs"], segs)
         n += 1
     assert n >= 8
+
+
+def test_predictor_surface_matches_reference_names():
+    """The inner predictor entry keeps the reference's parameter names and order (models/diffusion.py:478-491), the wrapper class its
+    method names (mid_sim_wrapper.py:172-509); unsupported modes are refused before any device work."""
+    import inspect
+    from snb import _capi
+    from snb.jmid import DiffusionTraj
+    from snb.jmid.forecaster import HumanTrajectoryForecasterSim
+    params = list(inspect.signature(DiffusionTraj.sample_sicnav_inference).parameters)
+    assert params[:12] == ["self", "num_points", "context", "sample", "bestof", "point_dim", "flexibility", "ret_traj", "sampling", "step",
+                           "with_constraints", "dynamics"]
+    sig = inspect.signature(DiffusionTraj.sample_sicnav_inference)
+    assert sig.parameters["sampling"].default == "ddpm" and sig.parameters["step"].default == 100      # the reference's defaults
+    for name in ("update_state_hists", "predict_ret_best", "predict", "get_most_likely_samples"):
+        assert callable(getattr(HumanTrajectoryForecasterSim, name))
+    assert list(inspect.signature(HumanTrajectoryForecasterSim.__init__).parameters)[1:3] == ["env_config", "mid_config_file"]
+    d = DiffusionTraj({}, joint=True)
+    import torch
+    ctx = torch.zeros(2, 256)
+    for bad in (dict(sampling="ddpm"), dict(sampling="ddim", ret_traj=True), dict(sampling="ddim", point_dim=3), dict(sampling="ddim", step=30),
+                dict(sampling="ddim", step=0)):
+        with pytest.raises(_capi.SnbError):
+            d.sample_sicnav_inference(8, ctx, 4, True, **bad)
+    with pytest.raises(_capi.SnbError):
+        d.sample_sicnav_inference(8, torch.zeros(2, 128), 4, True, sampling="ddim", step=20)
