@@ -190,47 +190,63 @@ __global__ void layernorm_kernel(const bf16 *__restrict__ pre, const bf16 *__res
 }
 
 // `linear` ConcatSquash 128 -> 2 on the concat4 output, then the DDIM update (diffusion.py:524-528).
-// 8 lanes per token (16 columns each), 4 tokens per warp.
-__global__ void tail_ddim_kernel(const bf16 *__restrict__ t4, const float *__restrict__ wl, const float *__restrict__ bl,
-                                 const float *__restrict__ gate, const float *__restrict__ hb, int tab_ld,
-                                 const float *__restrict__ x_t, float *__restrict__ x_next, float *__restrict__ eps_out,
-                                 int n_tok_total, int tok_per_env, int T, int A, float c1, float c2, float c3, float c4)
+// 8 lanes per token (16 columns each), 4 tokens per warp; a thread keeps the 32 weights of its 16 columns in registers and walks
+// TAIL_TOK_ITERS tokens with them (it used to issue 64 scalar weight loads per token next to the two 16-byte data loads).  Same
+// accumulation order per lane and the same shuffle tree as before, hence the same bits.
+constexpr int TAIL_TOK_ITERS = 8;
+__global__ void __launch_bounds__(256) tail_ddim_kernel(const bf16 *__restrict__ t4, const float *__restrict__ wl, const float *__restrict__ bl,
+                                                        const float *__restrict__ gate, const float *__restrict__ hb, int tab_ld,
+                                                        const float *__restrict__ x_t, float *__restrict__ x_next, float *__restrict__ eps_out,
+                                                        int n_tok_total, int tok_per_env, int T, int A, float c1, float c2, float c3, float c4)
 {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int tok = gid >> 3, sub = gid & 7;
-    const bool ok = tok < n_tok_total;
-    float a0 = 0.0f, a1 = 0.0f;
-    if (ok) {
-        const uint4 *p = reinterpret_cast<const uint4 *>(t4 + (size_t)tok * 128 + sub * 16);
+    const int sub = threadIdx.x & 7;
+    float w0[16], w1[16];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const uint4 u = p[q];
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int q = 0; q < 4; ++q) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(wl + sub * 16) + q);
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(wl + 128 + sub * 16) + q);
+        w0[4 * q] = a.x; w0[4 * q + 1] = a.y; w0[4 * q + 2] = a.z; w0[4 * q + 3] = a.w;
+        w1[4 * q] = b.x; w1[4 * q + 1] = b.y; w1[4 * q + 2] = b.z; w1[4 * q + 3] = b.w;
+    }
+    const float bl0 = bl[0], bl1 = bl[1];
+    const int tok0 = blockIdx.x * (32 * TAIL_TOK_ITERS) + (threadIdx.x >> 3);
+#pragma unroll 2
+    for (int it = 0; it < TAIL_TOK_ITERS; ++it) {
+        const int tok = tok0 + it * 32;
+        const bool ok = tok < n_tok_total;
+        float a0 = 0.0f, a1 = 0.0f;
+        if (ok) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(t4 + (size_t)tok * 128 + sub * 16);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162 *>(&w[i]);
-                const int k = sub * 16 + q * 8 + 2 * i;
-                const float f0 = __bfloat162float(v.x), f1 = __bfloat162float(v.y);
-                a0 = fmaf(f0, __ldg(wl + k), a0); a0 = fmaf(f1, __ldg(wl + k + 1), a0);
-                a1 = fmaf(f0, __ldg(wl + 128 + k), a1); a1 = fmaf(f1, __ldg(wl + 128 + k + 1), a1);
+            for (int q = 0; q < 2; ++q) {
+                const uint4 u = p[q];
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162 *>(&w[i]);
+                    const int k = q * 8 + 2 * i;
+                    const float f0 = __bfloat162float(v.x), f1 = __bfloat162float(v.y);
+                    a0 = fmaf(f0, w0[k], a0); a0 = fmaf(f1, w0[k + 1], a0);
+                    a1 = fmaf(f0, w1[k], a1); a1 = fmaf(f1, w1[k + 1], a1);
+                }
             }
         }
-    }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
-    if (ok && sub == 0) {
-        const int b = tok / tok_per_env;
-        const int r = (tok - b * tok_per_env) / T;
-        const int ba = b * A + (r % A);
-        const float *gp = gate + (size_t)ba * tab_ld, *hp = hb + (size_t)ba * tab_ld;
-        const float e0 = (a0 + bl[0]) * gp[0] + hp[0];
-        const float e1 = (a1 + bl[1]) * gp[1] + hp[1];
-        if (eps_out) { eps_out[2 * (size_t)tok] = e0; eps_out[2 * (size_t)tok + 1] = e1; }
-        if (x_next) {
-            const float x0 = x_t[2 * (size_t)tok], x1 = x_t[2 * (size_t)tok + 1];
-            const float p0 = (x0 - e0 * c1) / c2, p1 = (x1 - e1 * c1) / c2;   // x0_t
-            x_next[2 * (size_t)tok] = c3 * p0 + c4 * e0;
-            x_next[2 * (size_t)tok + 1] = c3 * p1 + c4 * e1;
+        for (int o = 4; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+        if (ok && sub == 0) {
+            const int b = tok / tok_per_env;
+            const int r = (tok - b * tok_per_env) / T;
+            const int ba = b * A + (r % A);
+            const float *gp = gate + (size_t)ba * tab_ld, *hp = hb + (size_t)ba * tab_ld;
+            const float e0 = (a0 + bl0) * gp[0] + hp[0];
+            const float e1 = (a1 + bl1) * gp[1] + hp[1];
+            if (eps_out) { eps_out[2 * (size_t)tok] = e0; eps_out[2 * (size_t)tok + 1] = e1; }
+            if (x_next) {
+                const float x0 = x_t[2 * (size_t)tok], x1 = x_t[2 * (size_t)tok + 1];
+                const float p0 = (x0 - e0 * c1) / c2, p1 = (x1 - e1 * c1) / c2;   // x0_t
+                x_next[2 * (size_t)tok] = c3 * p0 + c4 * e0;
+                x_next[2 * (size_t)tok + 1] = c3 * p1 + c4 * e1;
+            }
         }
     }
 }
@@ -317,8 +333,8 @@ int snb_k_tail_ddim(const bf16 *t4, const float *wl, const float *bl, const floa
                     const float *x_t, float *x_next, float *eps_out, int n_tok_total, int tok_per_env, int T, int A,
                     float c1, float c2, float c3, float c4, cudaStream_t s)
 {
-    const long long threads = (long long)n_tok_total * 8;
-    tail_ddim_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(t4, wl, bl, gate, hb, tab_ld, x_t, x_next, eps_out, n_tok_total,
+    const int tok_per_block = 32 * TAIL_TOK_ITERS;
+    tail_ddim_kernel<<<(unsigned)((n_tok_total + tok_per_block - 1) / tok_per_block), 256, 0, s>>>(t4, wl, bl, gate, hb, tab_ld, x_t, x_next, eps_out, n_tok_total,
                                                                        tok_per_env, T, A, c1, c2, c3, c4);
     snb_count_launch();
     SNB_CUDA_TRY(cudaGetLastError());
