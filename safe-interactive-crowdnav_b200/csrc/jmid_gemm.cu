@@ -356,7 +356,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int half = (warp - 2) >> 2;        // which half of the tile's BN columns this warp drains
         const int etid = (warp - 2) * 32 + lane;
         uint8_t *stg = smem + Cfg::OFF_STAGING + (warp - 2) * STAGING_BYTES;
-        int it = 0;
+        int it = 0, bias_n0 = -1;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -370,10 +370,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int r = (row - b * ep.tok_per_env) / ep.T;
                 ba = b * ep.A + (r % ep.A);
             }
-            // this tile's bias slice -> smem (the previous tile's readers are past their last use: barrier below)
-            tc::named_bar_sync(1, EPI_WARPS * 32);
-            for (int i = etid; i < BN; i += EPI_WARPS * 32) s_bias[i] = __ldg(ep.bias + n0 + i);
-            tc::named_bar_sync(1, EPI_WARPS * 32);
+            // this tile's bias slice -> smem, only when the column block changed (concat4, N = 128, has ONE column block: filled once);
+            // the previous tile's readers are past their last use: barrier below
+            if (n0 != bias_n0) {
+                tc::named_bar_sync(1, EPI_WARPS * 32);
+                for (int i = etid; i < BN; i += EPI_WARPS * 32) s_bias[i] = __ldg(ep.bias + n0 + i);
+                tc::named_bar_sync(1, EPI_WARPS * 32);
+                bias_n0 = n0;
+            }
 
             tc::mbar_wait(&tfull[acc], acc_phase);
             __syncwarp();                 // reconverge before the .sync.aligned TMEM loads
