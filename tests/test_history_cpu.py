@@ -70,3 +70,28 @@ def test_truncation_of_time_times_100_follows_pandas():
     rng = np.random.default_rng(5)
     hum, rob = _lists(rng, 2, times)
     _check(hum, rob, 0.25)
+
+
+def test_random_recordings_match_pandas_hypothesis():
+    """Property form: arbitrary (sorted, unique) time stamps on a 10 ms grid, arbitrary drops per agent."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @hyp.settings(max_examples=60, deadline=None, suppress_health_check=list(hyp.HealthCheck))
+    @hyp.given(ticks=st.lists(st.integers(min_value=-400, max_value=2000), min_size=2, max_size=40, unique=True),
+               H=st.integers(min_value=1, max_value=5), dt=st.sampled_from([0.25, 0.2, 0.1, 0.5]), seed=st.integers(0, 2 ** 16),
+               drop=st.sampled_from([0.0, 0.1, 0.3]))
+    def run(ticks, H, dt, seed, drop):
+        rng = np.random.default_rng(seed)
+        times = np.sort(np.asarray(ticks, np.float64)) * 0.01
+        hum, rob = _lists(rng, H, times, drop=drop)
+        if not rob or any(not h for h in hum):
+            return
+        common = set(t for _, _, t in rob)
+        for h in hum:
+            common &= set(t for _, _, t in h)
+        if not common or min(t for _, _, t in hum[0]) not in [t for _, _, t in hum[0]]:
+            return
+        _check(hum, rob, dt)
+
+    run()
